@@ -1,0 +1,198 @@
+/*
+ * trueknn.h — C ABI of libtrueknn: the B200-native (sm_100a) replacement for the hot path of
+ * vani-nag/OWLRayTracing's samples/s01-trueknn (TrueKNN): accel build -> traverse / intersect /
+ * k-list -> radius-doubling rounds.  Citations are relative to the reference repository root.
+ *
+ * The reference has no kNN library interface: its sample drives ~25 OWL C-API calls
+ * (owl/include/owl/owl_host.h:336-1240, call sites samples/s01-trueknn/hostCode.cpp:141-362).
+ * Each entry point below names the slice of that sequence it replaces.
+ *
+ * Conventions (all functions): plain pointers and sizes, no C++ types; returns TKNN_OK (0) or a
+ * TKNN_E* code and never throws or exits (the reference throws std::runtime_error through
+ * extern "C" — owl/helper/cuda.h:22-31 — and exit(2)s on OptiX errors — owl/helper/optix.h:34-42);
+ * the message of the last failure is available from tknn_last_error().  A context is bound to one
+ * CUDA device and is not thread-safe; distinct contexts are independent.  Input/output arrays may
+ * be HOST or DEVICE pointers (detected with cudaPointerGetAttributes); host buffers are staged
+ * through device memory inside the call.  Calls are synchronous on return, like owlLaunch2D
+ * (owl/impl.cpp:168-176).  There is no CPU fallback: without a CUDA device tknn_create fails.
+ *
+ * Result semantics (north star): for query q the k data points p != q BY INDEX minimising
+ * (d2(q,p), index(p)) lexicographically, d2 = fmaf(dz,dz,fmaf(dy,dy,dx*dx)) in fp32;
+ * idx_out[q*k+i] ascending, dist_out[q*k+i] = sqrtf(d2); unfilled slots are -1 / FLT_MAX
+ * (hostCode.cpp:129).  Indices refer to the order of the points passed to tknn_build
+ * (= file order in the sample, hostCode.cpp:115-124).
+ */
+#ifndef TRUEKNN_H
+#define TRUEKNN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define TKNN_API
+#else
+#define TKNN_API __attribute__((visibility("default")))
+#endif
+
+#define TKNN_VERSION 100
+
+enum {
+  TKNN_OK = 0,
+  TKNN_EINVAL = 1, /* bad argument (k >= n, dim not 2|3, non-finite coordinate, ...) */
+  TKNN_ENOMEM = 2, /* host or device allocation failed */
+  TKNN_ECUDA = 3,  /* CUDA runtime error (text in tknn_last_error) */
+  TKNN_ENCCL = 4,  /* reserved for the multi-GPU drivers */
+  TKNN_ESTATE = 5  /* call order (search before build, ...) */
+};
+
+#define TKNN_MAX_K 512
+#define TKNN_MAX_ROUNDS 48
+
+/* option keys for tknn_set_option */
+enum {
+  TKNN_OPT_LEAF_SIZE = 1,   /* max points per BVH leaf, 4..32 (default 32)                         */
+  TKNN_OPT_COUNTERS = 2,    /* 1: run the counting variant of the traversal kernel (V/T of §8d)   */
+  TKNN_OPT_LEAF_POLICY = 3, /* 0: Morton-aligned maximal subtrees (default); 1: fixed chunks       */
+  TKNN_OPT_SAMPLE_GROUPS = 4, /* groups of 32 queries sampled by the start-radius estimator (128) */
+  TKNN_OPT_BLOCKS_PER_SM = 5, /* persistent-grid size of the traversal kernel, 0 = auto            */
+  TKNN_OPT_SQUARED_DIST = 6,  /* 1: dist_out receives d2 instead of sqrtf(d2)                      */
+  TKNN_OPT_RADIUS_QUANTILE = 7 /* start-radius estimator: per-mille quantile of the sampled k-th
+                                  neighbour distance (default 990)                                */
+};
+
+typedef struct tknn_ctx tknn_ctx;
+
+typedef struct tknn_stats {
+  /* build (replaces "Build time", hostCode.cpp:201-212) */
+  uint64_t n_points;
+  uint32_t n_leaves;
+  uint32_t n_nodes;
+  float build_ms;     /* points on device -> BVH ready (sum of the phases below) */
+  float bounds_ms;    /* scene AABB reduce                                        */
+  float morton_ms;    /* Morton codes                                             */
+  float sort_ms;      /* onesweep radix sort (8 passes)                           */
+  float leaves_ms;    /* leaf cut + point gather                                  */
+  float hierarchy_ms; /* Karras hierarchy                                         */
+  float refit_ms;     /* bottom-up AABB refit                                     */
+  float h2d_ms;       /* host->device staging of the points (0 for device input)  */
+  /* last search (replaces "True KNN time", hostCode.cpp:279-347) */
+  uint64_t n_queries;
+  int32_t k;
+  int32_t rounds;
+  float start_radius; /* the radius round 1 ran with (after auto-estimation)      */
+  float final_radius;
+  float estimate_ms;  /* start-radius estimator (0 when the caller gave a radius) */
+  float search_ms;    /* first launch -> last result written on device, all rounds, incl. estimate */
+  float d2h_ms;       /* device->host copy of results (0 for device output)       */
+  float round_ms[TKNN_MAX_ROUNDS];
+  uint64_t round_queries[TKNN_MAX_ROUNDS]; /* queries active in each round */
+  uint32_t kernel_launches; /* kernels launched by the last search */
+  uint32_t build_launches;  /* kernels launched by the last build  */
+  /* counters (TKNN_OPT_COUNTERS=1), summed over all rounds; per-query, i.e. a 32-query group
+   * visiting a node counts once per active query (V(q), T(q)) */
+  uint64_t nodes_visited;   /* sum_q V(q): 64-byte node records a query's warp read           */
+  uint64_t points_tested;   /* sum_q T(q): float4 points distance-tested per query            */
+  uint64_t heap_inserts;    /* accepted candidates                                            */
+  uint64_t warp_node_visits;/* node records actually loaded (once per warp)                   */
+  uint64_t warp_leaf_visits;/* leaves actually loaded (once per warp)                         */
+  uint64_t warp_point_loads;/* float4 points actually loaded (once per warp)                  */
+  uint64_t h2d_bytes, d2h_bytes; /* staging traffic of the last build / search */
+} tknn_stats;
+
+/* Replaces owlContextCreate + module/program/pipeline/SBT setup (hostCode.cpp:141-159,267-269).
+ * device = CUDA ordinal.  Fails with TKNN_ECUDA when no usable device exists. */
+TKNN_API int tknn_create(int device, tknn_ctx** out);
+
+/* Replaces owlContextDestroy (hostCode.cpp:362): frees every device allocation of the context. */
+TKNN_API int tknn_destroy(tknn_ctx* ctx);
+
+/* Run all work of this context on `cuda_stream` (a cudaStream_t; NULL = the context's own
+ * non-blocking stream).  The reference uses one stream per LaunchParams (owl/LaunchParams.cpp:46). */
+TKNN_API int tknn_set_stream(tknn_ctx* ctx, void* cuda_stream);
+
+TKNN_API int tknn_set_option(tknn_ctx* ctx, int key, int64_t value);
+
+/* Replaces owlDeviceBufferCreate(points) + owlUserGeomGroupCreate + owlGroupBuildAccel(GAS) +
+ * owlInstanceGroupCreate + owlGroupBuildAccel(IAS) (hostCode.cpp:165-175,199-212), i.e.
+ * UserGeomGroup::buildAccel (owl/UserGeomGroup.cpp:39-241) and the bounds program
+ * (deviceCode.cu:38-56): builds an LBVH over the n points.
+ * xyz: n rows of `stride_floats` floats (>= dim); dim 2 => z = 0 (hostCode.cpp:114-118), dim 3. */
+TKNN_API int tknn_build(tknn_ctx* ctx, const float* xyz, uint64_t n, int dim, int stride_floats);
+
+/* Replaces the whole round loop (hostCode.cpp:285-340: owlLaunch2D + host termination scan +
+ * radius *= 2 + 2x owlGroupRefitAccel) and the raygen / intersection programs
+ * (deviceCode.cu:62-152).  All n points are the queries (samples/s01-trueknn/README.md:2).
+ * start_radius > 0: round 1 searches the closed ball of that radius, unresolved queries double it
+ * (hostCode.cpp:323); start_radius <= 0: estimated from a sample (Util/random_sample.py's role);
+ * start_radius = +inf: one unbounded round.  idx_out/dist_out: n*k each, rows in build order.
+ * k must satisfy 1 <= k <= min(n-1, TKNN_MAX_K) (the reference never terminates for k > n-1). */
+TKNN_API int tknn_search(tknn_ctx* ctx, int k, float start_radius, int32_t* idx_out, float* dist_out);
+
+/* Query-sharded variant: this context answers shard `shard` of `n_shards`
+ * contiguous Morton slices of the queries over its (replicated) BVH.  Rows are written compactly:
+ * row r holds the neighbours of query qid_out[r]; *n_out rows are produced.  Capacity of each
+ * output array must be at least tknn_shard_capacity(n, n_shards) rows. */
+TKNN_API int tknn_search_shard(tknn_ctx* ctx, int k, float start_radius, int shard, int n_shards, int32_t* qid_out,
+                               int32_t* idx_out, float* dist_out, uint64_t* n_out);
+TKNN_API uint64_t tknn_shard_capacity(uint64_t n, int n_shards);
+
+/* Separate query set on the built BVH.  queries: nq rows; self_ids (may be
+ * NULL) names the data index to exclude per query (-1: none); init_radius (may be NULL): per-query
+ * closed search radius (used by the point-partitioned driver for boundary queries).
+ * Output rows follow the query order. */
+TKNN_API int tknn_query(tknn_ctx* ctx, const float* queries, uint64_t nq, int dim, int stride_floats,
+                        const int32_t* self_ids, const float* init_radius, int k, float start_radius,
+                        int32_t* idx_out, float* dist_out);
+
+/* Fixed-radius neighbour count per point (closed ball, self excluded) on the same traversal
+ * (the DBSCAN core-point test).  count_out: n entries, build order. */
+TKNN_API int tknn_range_count(tknn_ctx* ctx, float radius, uint32_t* count_out);
+
+/* Start-radius estimator alone (replaces samples/s01-trueknn/Util/random_sample.py:5-32). */
+TKNN_API int tknn_estimate_start_radius(tknn_ctx* ctx, int k, float* radius_out);
+
+/* Exact brute-force kNN of selected data points on the GPU (tiled, no BVH): the second oracle for
+ * sampled queries at sizes no CPU oracle reaches.  query_ids: nq data
+ * indices (host or device).  Output rows follow query_ids. */
+TKNN_API int tknn_brute_force(tknn_ctx* ctx, const int32_t* query_ids, uint64_t nq, int k, int32_t* idx_out,
+                              float* dist_out);
+
+/* k-way merge of partial neighbour lists on (d2, index): for each of nq rows, merge `parts` lists
+ * of k (idx, d2) pairs (layout [parts][nq][k], a list ends at its first -1 index, duplicates by
+ * index removed) into one list of k.  d2_parts holds SQUARED distances (produced with
+ * TKNN_OPT_SQUARED_DIST = 1: sqrtf is not injective, so only d2 gives the exact order); dist_out
+ * receives sqrtf(d2).  Used by the point-partitioned driver. */
+TKNN_API int tknn_merge_topk(tknn_ctx* ctx, const int32_t* idx_parts, const float* d2_parts, int parts, uint64_t nq,
+                             int k, int32_t* idx_out, float* dist_out);
+
+TKNN_API int tknn_get_stats(const tknn_ctx* ctx, tknn_stats* out);
+TKNN_API const char* tknn_last_error(const tknn_ctx* ctx);
+TKNN_API int tknn_version(void);
+
+/* ---- introspection used by the tests and the bench (not part of the drop-in surface) ---- */
+
+/* Stand-alone onesweep radix sort of (u64 key, u32 value) pairs, stable, in place; device or host
+ * pointers. */
+TKNN_API int tknn_sort_pairs(tknn_ctx* ctx, uint64_t* keys, uint32_t* values, uint64_t n);
+
+/* Copies of the built BVH: nodes (n_nodes x 16 words), sorted points
+ * (n x float4: x, y, z, original index bits), leaf starts (n_leaves + 1).  NULL pointers skipped. */
+TKNN_API int tknn_get_bvh(const tknn_ctx* ctx, void* nodes_out, void* points_out, uint32_t* leaf_start_out);
+
+/* Synthetic clouds generated on the device by the stateless hash of SURVEY.md §8d:
+ * u(i,a) = (mix64(seed ^ ((3i+a) * 0x9E3779B97F4A7C15)) >> 40) * 2^-24.  Writes n rows of xyz
+ * for indices [first, first+n) to a DEVICE or HOST array. */
+TKNN_API int tknn_generate_uniform(tknn_ctx* ctx, uint64_t seed, uint64_t first, uint64_t n, float* xyz_out);
+
+/* Device properties the roofline needs: SM count, L2 bytes, and a measured L2 / HBM read
+ * bandwidth (GB/s) from a short read loop over an L2-resident / HBM-sized buffer. */
+TKNN_API int tknn_measure_bandwidth(tknn_ctx* ctx, double* l2_gbs, double* hbm_gbs, int* sm_count, uint64_t* l2_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRUEKNN_H */

@@ -1,0 +1,116 @@
+"""ctypes loader for libtrueknn.so (include/trueknn.h).
+
+There is no CPU fallback: if the shared library is missing this raises, and if no CUDA device is
+usable `tknn_create` fails and `TrueKNN(...)` raises.  The library is built in-tree by
+`__graft_entry__.build()` (or `make -C owlraytracing_b200/csrc`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtrueknn.so")
+
+TKNN_MAX_ROUNDS = 48
+TKNN_MAX_K = 512
+
+OK, EINVAL, ENOMEM, ECUDA, ENCCL, ESTATE = 0, 1, 2, 3, 4, 5
+ERROR_NAMES = {0: "TKNN_OK", 1: "TKNN_EINVAL", 2: "TKNN_ENOMEM", 3: "TKNN_ECUDA", 4: "TKNN_ENCCL", 5: "TKNN_ESTATE"}
+
+OPT_LEAF_SIZE, OPT_COUNTERS, OPT_LEAF_POLICY, OPT_SAMPLE_GROUPS, OPT_BLOCKS_PER_SM, OPT_SQUARED_DIST, OPT_RADIUS_QUANTILE = (
+    1, 2, 3, 4, 5, 6, 7)
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("n_points", C.c_uint64),
+        ("n_leaves", C.c_uint32),
+        ("n_nodes", C.c_uint32),
+        ("build_ms", C.c_float),
+        ("bounds_ms", C.c_float),
+        ("morton_ms", C.c_float),
+        ("sort_ms", C.c_float),
+        ("leaves_ms", C.c_float),
+        ("hierarchy_ms", C.c_float),
+        ("refit_ms", C.c_float),
+        ("h2d_ms", C.c_float),
+        ("n_queries", C.c_uint64),
+        ("k", C.c_int32),
+        ("rounds", C.c_int32),
+        ("start_radius", C.c_float),
+        ("final_radius", C.c_float),
+        ("estimate_ms", C.c_float),
+        ("search_ms", C.c_float),
+        ("d2h_ms", C.c_float),
+        ("round_ms", C.c_float * TKNN_MAX_ROUNDS),
+        ("round_queries", C.c_uint64 * TKNN_MAX_ROUNDS),
+        ("kernel_launches", C.c_uint32),
+        ("build_launches", C.c_uint32),
+        ("nodes_visited", C.c_uint64),
+        ("points_tested", C.c_uint64),
+        ("heap_inserts", C.c_uint64),
+        ("warp_node_visits", C.c_uint64),
+        ("warp_leaf_visits", C.c_uint64),
+        ("warp_point_loads", C.c_uint64),
+        ("h2d_bytes", C.c_uint64),
+        ("d2h_bytes", C.c_uint64),
+    ]
+
+    def as_dict(self) -> dict:
+        d = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            if name in ("round_ms", "round_queries"):
+                v = list(v)[: max(0, int(self.rounds))]
+            d[name] = v
+        return d
+
+
+# every symbol include/trueknn.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "tknn_create", "tknn_destroy", "tknn_set_stream", "tknn_set_option", "tknn_build", "tknn_search",
+    "tknn_search_shard", "tknn_shard_capacity", "tknn_query", "tknn_range_count", "tknn_estimate_start_radius",
+    "tknn_brute_force", "tknn_merge_topk", "tknn_get_stats", "tknn_last_error", "tknn_version", "tknn_sort_pairs",
+    "tknn_get_bvh", "tknn_generate_uniform", "tknn_measure_bandwidth",
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libtrueknn.so and declare the prototypes. Raises OSError when it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OSError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u32, u64, f32 = C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, C.c_float
+    L.tknn_version.restype = C.c_int
+    L.tknn_last_error.restype = C.c_char_p
+    L.tknn_last_error.argtypes = [vp]
+    L.tknn_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.tknn_destroy.argtypes = [vp]
+    L.tknn_set_stream.argtypes = [vp, vp]
+    L.tknn_set_option.argtypes = [vp, C.c_int, C.c_int64]
+    L.tknn_build.argtypes = [vp, vp, u64, C.c_int, C.c_int]
+    L.tknn_search.argtypes = [vp, C.c_int, f32, vp, vp]
+    L.tknn_search_shard.argtypes = [vp, C.c_int, f32, C.c_int, C.c_int, vp, vp, vp, C.POINTER(u64)]
+    L.tknn_shard_capacity.restype = u64
+    L.tknn_shard_capacity.argtypes = [u64, C.c_int]
+    L.tknn_query.argtypes = [vp, vp, u64, C.c_int, C.c_int, vp, vp, C.c_int, f32, vp, vp]
+    L.tknn_range_count.argtypes = [vp, f32, vp]
+    L.tknn_estimate_start_radius.argtypes = [vp, C.c_int, C.POINTER(f32)]
+    L.tknn_brute_force.argtypes = [vp, vp, u64, C.c_int, vp, vp]
+    L.tknn_merge_topk.argtypes = [vp, vp, vp, C.c_int, u64, C.c_int, vp, vp]
+    L.tknn_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.tknn_sort_pairs.argtypes = [vp, vp, vp, u64]
+    L.tknn_get_bvh.argtypes = [vp, vp, vp, vp]
+    L.tknn_generate_uniform.argtypes = [vp, u64, u64, u64, vp]
+    L.tknn_measure_bandwidth.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int),
+                                         C.POINTER(u64)]
+    _lib = L
+    return L

@@ -1,0 +1,200 @@
+// brute.cuh — exact tiled brute-force kNN (no BVH), the k-way list merge, the synthetic generator
+// and the bandwidth probe.
+//
+// The brute-force kernel is the GPU-side second oracle for sampled queries at sizes no CPU oracle
+// reaches.  It shares the distance formula, key order and heap with the
+// traversal kernel but none of its culling logic, so a culling bug cannot hide in both.
+#pragma once
+#include "common.cuh"
+#include "traverse.cuh"
+
+namespace tknn {
+namespace brute {
+
+// Finds the sorted position of each requested original index: ids_sorted ascending, nq entries.
+// qpts[rank] = (x, y, z, original index bits).
+__global__ void __launch_bounds__(256) lookup_queries_kernel(const float4* __restrict__ pts, uint64_t n,
+                                                             const int32_t* __restrict__ ids_sorted, uint32_t nq,
+                                                             float4* __restrict__ qpts) {
+  const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(&pts[i]);
+  const int id = __float_as_int(p.w);
+  uint32_t lo = 0, hi = nq;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (ids_sorted[mid] < id) lo = mid + 1; else hi = mid;
+  }
+  if (lo < nq && ids_sorted[lo] == id) qpts[lo] = p;
+}
+
+// One warp per (group of 32 queries, split of the point range).  partial[(split * nq + q) * k + i]
+// receives the ascending key list (~0 = empty slot).
+__global__ void __launch_bounds__(32) brute_kernel(const float4* __restrict__ pts, uint64_t n,
+                                                   const float4* __restrict__ qpts, uint32_t nq, int k, int splits,
+                                                   uint64_t* __restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float4* stage = reinterpret_cast<float4*>(smem);
+  const int lane = threadIdx.x;
+  uint64_t* H = reinterpret_cast<uint64_t*>(smem + 32 * sizeof(float4)) + lane;
+  const uint32_t group = blockIdx.x;
+  const int split = blockIdx.y;
+  const uint32_t qi = group * 32 + lane;
+  const bool valid = qi < nq;
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid) q = qpts[qi];
+  const int self = __float_as_int(q.w);
+  const uint64_t chunk = (((n + splits - 1) / splits) + 31) / 32 * 32;
+  const uint64_t begin = (uint64_t)split * chunk;
+  const uint64_t end = begin + chunk < n ? begin + chunk : n;
+  int cnt = 0;
+  float bound = valid ? INFINITY : -1.0f;
+  for (uint64_t base = begin; base < end; base += 32) {
+    const int m = (int)((end - base) < 32 ? (end - base) : 32);
+    if (lane < m) stage[lane] = __ldg(&pts[base + lane]);
+    __syncwarp();
+    uint32_t mask = 0;
+    for (int j = 0; j < m; ++j) {
+      const float4 p = stage[j];
+      const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+      mask |= (d <= bound ? 1u : 0u) << j;
+    }
+    while (mask) {
+      const int j = __ffs(mask) - 1;
+      mask &= mask - 1u;
+      const float4 p = stage[j];
+      const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+      const int pid = __float_as_int(p.w);
+      if (pid == self) continue;
+      const uint64_t key = make_key(d, pid);
+      if (cnt < k) {
+        trav::heap_push(H, cnt, key);
+        if (cnt == k) bound = key_d2(H[0]);
+      } else if (key < H[0]) {
+        trav::heap_sift_root(H, k, key);
+        bound = key_d2(H[0]);
+      }
+    }
+    __syncwarp();
+  }
+  if (valid) {
+    uint64_t* out = partial + ((uint64_t)split * nq + qi) * (uint64_t)k;
+    for (int i = k - 1; i >= cnt; --i) out[i] = ~0ull;
+    for (int i = cnt - 1; i >= 0; --i) {
+      out[i] = H[0];
+      if (i > 0) trav::heap_sift_root(H, i, H[i * 32]);
+    }
+  }
+}
+
+// Merge `parts` ascending key lists per query into one; writes (idx, sqrt(d2)) rows.
+// row_of[q] (optional) redirects the output row.
+__global__ void __launch_bounds__(32) merge_keys_kernel(const uint64_t* __restrict__ partial, int parts, uint32_t nq, int k,
+                                                        const uint32_t* __restrict__ row_of, int32_t* __restrict__ idx_out,
+                                                        float* __restrict__ dist_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x;
+  uint64_t* H = reinterpret_cast<uint64_t*>(smem) + lane;
+  const uint32_t qi = blockIdx.x * 32 + lane;
+  if (qi >= nq) return;
+  int cnt = 0;
+  for (int s = 0; s < parts; ++s) {
+    const uint64_t* in = partial + ((uint64_t)s * nq + qi) * (uint64_t)k;
+    for (int i = 0; i < k; ++i) {
+      const uint64_t key = in[i];
+      if (key == ~0ull) break;
+      if (cnt < k) trav::heap_push(H, cnt, key);
+      else if (key < H[0]) trav::heap_sift_root(H, k, key);
+      else break;  // lists ascend: nothing smaller follows
+    }
+  }
+  const uint64_t row = row_of ? row_of[qi] : qi;
+  int32_t* io = idx_out + row * (uint64_t)k;
+  float* dd = dist_out + row * (uint64_t)k;
+  for (int i = k - 1; i >= cnt; --i) { io[i] = -1; dd[i] = FLT_MAX; }
+  for (int i = cnt - 1; i >= 0; --i) {
+    const uint64_t top = H[0];
+    io[i] = key_idx(top);
+    dd[i] = __fsqrt_rn(key_d2(top));
+    if (i > 0) trav::heap_sift_root(H, i, H[i * 32]);
+  }
+}
+
+// Merge of (idx, d2) partial lists (point-partitioned driver).  The partial lists
+// carry SQUARED distances (contexts run with TKNN_OPT_SQUARED_DIST = 1): sqrtf maps two adjacent
+// d2 values to one float about half of the time, so ordering on the reported distance would not
+// be the (d2, index) order.  Duplicates by index are dropped; the output distance is sqrtf(d2).
+__global__ void __launch_bounds__(32) merge_lists_kernel(const int32_t* __restrict__ idx_parts,
+                                                         const float* __restrict__ dist_parts, int parts, uint32_t nq, int k,
+                                                         int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x;
+  uint64_t* H = reinterpret_cast<uint64_t*>(smem) + lane;
+  const uint32_t qi = blockIdx.x * 32 + lane;
+  if (qi >= nq) return;
+  int cnt = 0;
+  for (int s = 0; s < parts; ++s) {
+    const uint64_t off = ((uint64_t)s * nq + qi) * (uint64_t)k;
+    for (int i = 0; i < k; ++i) {
+      const int id = idx_parts[off + i];
+      if (id < 0) break;
+      const uint64_t key = make_key(dist_parts[off + i], id);
+      bool dup = false;
+      for (int h = 0; h < cnt; ++h)
+        if (key_idx(H[h * 32]) == id) { dup = true; break; }
+      if (dup) continue;
+      if (cnt < k) trav::heap_push(H, cnt, key);
+      else if (key < H[0]) trav::heap_sift_root(H, k, key);
+    }
+  }
+  int32_t* io = idx_out + (uint64_t)qi * k;
+  float* dd = dist_out + (uint64_t)qi * k;
+  for (int i = k - 1; i >= cnt; --i) { io[i] = -1; dd[i] = FLT_MAX; }
+  for (int i = cnt - 1; i >= 0; --i) {
+    const uint64_t top = H[0];
+    io[i] = key_idx(top);
+    dd[i] = __fsqrt_rn(key_d2(top));
+    if (i > 0) trav::heap_sift_root(H, i, H[i * 32]);
+  }
+}
+
+// small gathers used by tknn_query to follow the Morton order of the queries
+__global__ void __launch_bounds__(256) gather_i32_kernel(const int32_t* __restrict__ in, const uint32_t* __restrict__ order,
+                                                         uint64_t n, int32_t* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) out[i] = in[order[i]];
+}
+__global__ void __launch_bounds__(256) gather_r2_kernel(const float* __restrict__ radius, const uint32_t* __restrict__ order,
+                                                        uint64_t n, float* __restrict__ r2_out) {
+  const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) {
+    const float r = radius[order[i]];
+    r2_out[i] = r >= 0.0f ? __fmul_rn(r, r) : INFINITY;  // negative = no cap
+  }
+}
+
+// u(i, a) = (mix64(seed ^ ((3 i + a) * phi64)) >> 40) * 2^-24  in [0, 1)   
+__global__ void __launch_bounds__(256) generate_uniform_kernel(uint64_t seed, uint64_t first, uint64_t n,
+                                                               float* __restrict__ xyz) {
+  const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= 3 * n) return;
+  const uint64_t c = 3 * first + t;  // = 3 i + a
+  const uint64_t h = mix64(seed ^ (c * 0x9E3779B97F4A7C15ull));
+  xyz[t] = (float)(h >> 40) * 5.9604644775390625e-08f;
+}
+
+// read-bandwidth probe: sums `words` uint4 per pass, `passes` passes
+__global__ void __launch_bounds__(256) read_probe_kernel(const uint4* __restrict__ buf, uint64_t words, int passes,
+                                                         uint32_t* __restrict__ sink) {
+  uint32_t acc = 0;
+  const uint64_t step = (uint64_t)gridDim.x * 256;
+  for (int p = 0; p < passes; ++p)
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < words; i += step) {
+      const uint4 v = __ldcg(&buf[i]);
+      acc += v.x ^ v.y ^ v.z ^ v.w;
+    }
+  if (acc == 0x12345678u) *sink = acc;
+}
+
+}  // namespace brute
+}  // namespace tknn

@@ -1,0 +1,356 @@
+// lbvh.cuh — LBVH builder kernels: scene bounds, Morton codes, leaf cut, Karras hierarchy, refit.
+//
+// Stands in for UserGeomGroup::buildAccel (owl/UserGeomGroup.cpp:39-241: bounds program +
+// optixAccelBuild) and the 1-instance IAS on top of it (owl/InstanceGroup.cpp:110-280).  Unlike
+// the reference's bounds program (samples/s01-trueknn/deviceCode.cu:38-48) the boxes here bound
+// the POINTS, not radius-inflated spheres: the search radius is a kernel argument of the
+// traversal, so nothing is rebuilt or refitted between rounds (hostCode.cpp:326-327 disappears).
+#pragma once
+#include "common.cuh"
+
+namespace tknn {
+namespace lbvh {
+
+constexpr int THREADS = 256;
+
+// ------------------------------------------------------------------------------------------------
+// scene AABB: warp-shuffle + block reduce, one atomicMin/Max per block on order-preserving uints.
+// Also flags non-finite coordinates (bad != 0 => tknn_build returns TKNN_EINVAL).
+// bounds[0..2] = ordered(min xyz), bounds[3..5] = ordered(max xyz), bounds[6] = bad flag.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS) bounds_kernel(const float* __restrict__ xyz, uint64_t n, int dim, int stride,
+                                                         uint32_t* __restrict__ bounds) {
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  int bad = 0;
+  const uint64_t step = (uint64_t)gridDim.x * THREADS;
+  for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += step) {
+    const float* p = xyz + i * (uint64_t)stride;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float v = (a < dim) ? p[a] : 0.0f;
+      if (!isfinite(v)) bad = 1;
+      lo[a] = fminf(lo[a], v);
+      hi[a] = fmaxf(hi[a], v);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(FULL_MASK, lo[a], o));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(FULL_MASK, hi[a], o));
+    }
+    bad |= __shfl_xor_sync(FULL_MASK, bad, o);
+  }
+  __shared__ float s_lo[THREADS / 32][3], s_hi[THREADS / 32][3];
+  __shared__ int s_bad[THREADS / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    for (int a = 0; a < 3; ++a) { s_lo[warp][a] = lo[a]; s_hi[warp][a] = hi[a]; }
+    s_bad[warp] = bad;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int a = threadIdx.x;
+    float l = s_lo[0][a], h = s_hi[0][a];
+    for (int w = 1; w < THREADS / 32; ++w) { l = fminf(l, s_lo[w][a]); h = fmaxf(h, s_hi[w][a]); }
+    atomicMin(&bounds[a], float_to_ordered(l));
+    atomicMax(&bounds[3 + a], float_to_ordered(h));
+  }
+  if (threadIdx.x == 3) {
+    int b = 0;
+    for (int w = 0; w < THREADS / 32; ++w) b |= s_bad[w];
+    if (b) atomicOr(&bounds[6], 1u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 63-bit Morton code (21 bits per axis) on a CUBIC grid spanning the longest scene extent, so
+// cells are cubes whatever the aspect ratio of the cloud.  vals[i] = i (the sort payload).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t spread21(uint32_t v) {
+  uint64_t x = v & 0x1fffffu;
+  x = (x | (x << 32)) & 0x001f00000000ffffull;
+  x = (x | (x << 16)) & 0x001f0000ff0000ffull;
+  x = (x | (x << 8)) & 0x100f00f00f00f00full;
+  x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
+  x = (x | (x << 2)) & 0x1249249249249249ull;
+  return x;
+}
+
+__global__ void __launch_bounds__(THREADS) morton_kernel(const float* __restrict__ xyz, uint64_t n, int dim, int stride,
+                                                         const uint32_t* __restrict__ bounds,
+                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
+  if (i >= n) return;
+  const float lx = ordered_to_float(bounds[0]), ly = ordered_to_float(bounds[1]), lz = ordered_to_float(bounds[2]);
+  const float ex = ordered_to_float(bounds[3]) - lx, ey = ordered_to_float(bounds[4]) - ly,
+              ez = ordered_to_float(bounds[5]) - lz;
+  const float ext = fmaxf(fmaxf(ex, ey), fmaxf(ez, FLT_MIN));
+  const float scale = 2097152.0f / ext;  // 2^21 cells along the longest axis
+  const float* p = xyz + i * (uint64_t)stride;
+  const float x = p[0], y = p[1], z = dim > 2 ? p[2] : 0.0f;
+  const uint32_t cx = (uint32_t)fminf(fmaxf((x - lx) * scale, 0.0f), 2097151.0f);
+  const uint32_t cy = (uint32_t)fminf(fmaxf((y - ly) * scale, 0.0f), 2097151.0f);
+  const uint32_t cz = (uint32_t)fminf(fmaxf((z - lz) * scale, 0.0f), 2097151.0f);
+  keys[i] = (spread21(cx) << 2) | (spread21(cy) << 1) | spread21(cz);
+  vals[i] = (uint32_t)i;
+}
+
+// sorted float4 points: (x, y, z, original index bits)
+__global__ void __launch_bounds__(THREADS) gather_points_kernel(const float* __restrict__ xyz, int dim, int stride,
+                                                                const uint32_t* __restrict__ order, uint64_t n,
+                                                                float4* __restrict__ pts) {
+  const uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t src = order[i];
+  const float* p = xyz + (uint64_t)src * (uint64_t)stride;
+  pts[i] = make_float4(p[0], p[1], dim > 2 ? p[2] : 0.0f, __uint_as_float(src));
+}
+
+// ------------------------------------------------------------------------------------------------
+// delta[b] = length of the common prefix of the augmented keys (code, position) at sorted positions
+// b-1 and b (Karras 2012); smaller = stronger split.  delta[0] = 0.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS) delta_kernel(const uint64_t* __restrict__ keys, uint64_t n,
+                                                        uint8_t* __restrict__ delta) {
+  const uint64_t b = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
+  if (b >= n) return;
+  if (b == 0) { delta[0] = 0; return; }
+  const uint64_t x = keys[b - 1] ^ keys[b];
+  delta[b] = (uint8_t)(x ? __clzll((long long)x) : 64 + __clz((uint32_t)(b - 1) ^ (uint32_t)b));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Leaf cut.  Policy 0 (default): the leaves are the maximal subtrees of the point-level radix tree
+// holding <= leaf_max points ("treelet collapse"), found WITHOUT building that tree: the internal
+// node that splits at boundary b spans the points between the nearest strictly stronger boundaries
+// on each side, and b is a leaf boundary iff that span exceeds leaf_max — a +-leaf_max window scan.
+// Policy 1: fixed chunks of leaf_max consecutive points.
+// Output: one ballot word per 32 boundaries.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS) leaf_flag_kernel(const uint8_t* __restrict__ delta, uint64_t n, int leaf_max,
+                                                            int policy, uint64_t force_split,
+                                                            uint32_t* __restrict__ ballots) {
+  const uint64_t b = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
+  bool cut = false;
+  if (b < n) {
+    if (b == 0 || (force_split && b == force_split)) cut = true;
+    else if (policy == 1) cut = (b % (uint64_t)leaf_max) == 0;
+    else {
+      const int s = delta[b];
+      const int64_t ib = (int64_t)b, in = (int64_t)n;
+      int64_t l = -1, r = -1;
+      int64_t jlo = ib - leaf_max + 1;
+      for (int64_t j = ib - 1; j >= 1 && j >= jlo; --j)
+        if (delta[j] < s) { l = j; break; }
+      if (l < 0 && jlo <= 0) l = 0;
+      int64_t jhi = ib + leaf_max - 1;
+      for (int64_t j = ib + 1; j <= in - 1 && j <= jhi; ++j)
+        if (delta[j] < s) { r = j; break; }
+      if (r < 0 && jhi >= in) r = in;
+      cut = (l < 0) || (r < 0) || (r - l > leaf_max);
+    }
+  }
+  const uint32_t w = __ballot_sync(FULL_MASK, cut);
+  if ((threadIdx.x & 31) == 0 && b < n) ballots[b >> 5] = w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exclusive scan of popc(ballots[i]) (three-phase reduce / scan-of-sums / apply).
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_CHUNK = THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(FULL_MASK, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint32_t off = 0, tot = 0;
+  for (int w = 0; w < THREADS / 32; ++w) {
+    const uint32_t x = s_warp[w];
+    if (w < warp) off += x;
+    tot += x;
+  }
+  __syncthreads();
+  if (total) *total = tot;
+  return off + inc - v;
+}
+
+__global__ void __launch_bounds__(THREADS) popc_reduce_kernel(const uint32_t* __restrict__ words, uint64_t nw,
+                                                              uint32_t* __restrict__ block_sums) {
+  __shared__ uint32_t s_warp[THREADS / 32];
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_CHUNK + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t v = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i)
+    if (base + i < nw) v += __popc(words[base + i]);
+  uint32_t total;
+  block_exclusive_scan(v, s_warp, &total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of block_sums in place, grand total -> *total_out
+__global__ void __launch_bounds__(THREADS) scan_sums_kernel(uint32_t* __restrict__ block_sums, uint32_t nb,
+                                                            uint32_t* __restrict__ total_out) {
+  __shared__ uint32_t s_warp[THREADS / 32];
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < nb; base += THREADS) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < nb ? block_sums[i] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan(v, s_warp, &total);
+    if (i < nb) block_sums[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(THREADS) popc_apply_kernel(const uint32_t* __restrict__ words, uint64_t nw,
+                                                             const uint32_t* __restrict__ block_sums,
+                                                             uint32_t* __restrict__ offsets) {
+  __shared__ uint32_t s_warp[THREADS / 32];
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_CHUNK + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t c[SCAN_ITEMS];
+  uint32_t v = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    c[i] = (base + i < nw) ? __popc(words[base + i]) : 0u;
+    v += c[i];
+  }
+  uint32_t ex = block_exclusive_scan(v, s_warp, nullptr) + block_sums[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    if (base + i < nw) offsets[base + i] = ex;
+    ex += c[i];
+  }
+}
+
+// leaf_start[offsets[w] + rank-in-word] = b for every flagged boundary; leaf_key = its Morton code
+__global__ void __launch_bounds__(THREADS) leaf_emit_kernel(const uint32_t* __restrict__ ballots,
+                                                            const uint32_t* __restrict__ offsets,
+                                                            const uint64_t* __restrict__ keys, uint64_t n,
+                                                            uint32_t n_leaves, uint32_t* __restrict__ leaf_start,
+                                                            uint64_t* __restrict__ leaf_key) {
+  const uint64_t b = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
+  if (b == 0) leaf_start[n_leaves] = (uint32_t)n;
+  if (b >= n) return;
+  const uint32_t w = ballots[b >> 5];
+  const int bit = (int)(b & 31);
+  if ((w >> bit) & 1u) {
+    const uint32_t pos = offsets[b >> 5] + __popc(w & ((1u << bit) - 1u));
+    leaf_start[pos] = (uint32_t)b;
+    leaf_key[pos] = keys[b];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Karras radix-tree hierarchy over the M leaves (keys = first Morton code of each leaf, ties broken
+// by leaf index).  One thread per internal node.  child_info[node] = (ref0, cnt0, ref1, cnt1):
+// cnt == 0 => internal child (ref = node index) else leaf child (ref = first sorted point).
+// parent_*[] = (parent node << 1) | child slot;  node 0 is the root.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int karras_delta(const uint64_t* __restrict__ key, int64_t m, int64_t i, int64_t j) {
+  if (j < 0 || j >= m) return -1;
+  const uint64_t x = key[i] ^ key[j];
+  return x ? __clzll((long long)x) : 64 + __clz((uint32_t)i ^ (uint32_t)j);
+}
+
+__global__ void __launch_bounds__(THREADS) karras_kernel(const uint64_t* __restrict__ leaf_key,
+                                                         const uint32_t* __restrict__ leaf_start, uint32_t n_leaves,
+                                                         int4* __restrict__ child_info, int32_t* __restrict__ parent_leaf,
+                                                         int32_t* __restrict__ parent_node) {
+  const int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x;
+  const int64_t m = n_leaves;
+  if (i >= m - 1) return;
+  const int d = (karras_delta(leaf_key, m, i, i + 1) - karras_delta(leaf_key, m, i, i - 1)) >= 0 ? 1 : -1;
+  const int dmin = karras_delta(leaf_key, m, i, i - d);
+  int64_t lmax = 2;
+  while (karras_delta(leaf_key, m, i, i + lmax * d) > dmin) lmax <<= 1;
+  int64_t l = 0;
+  for (int64_t t = lmax >> 1; t >= 1; t >>= 1)
+    if (karras_delta(leaf_key, m, i, i + (l + t) * d) > dmin) l += t;
+  const int64_t j = i + l * d;
+  const int dnode = karras_delta(leaf_key, m, i, j);
+  int64_t s = 0, t = l;
+  do {
+    t = (t + 1) >> 1;
+    if (karras_delta(leaf_key, m, i, i + (s + t) * d) > dnode) s += t;
+  } while (t > 1);
+  const int64_t gamma = i + s * d + (d < 0 ? -1 : 0);
+  const int64_t lo = i < j ? i : j, hi = i < j ? j : i;
+  int4 info;
+  if (lo == gamma) {
+    info.x = (int)leaf_start[gamma];
+    info.y = (int)(leaf_start[gamma + 1] - leaf_start[gamma]);
+    parent_leaf[gamma] = (int)((i << 1) | 0);
+  } else {
+    info.x = (int)gamma;
+    info.y = 0;
+    parent_node[gamma] = (int)((i << 1) | 0);
+  }
+  if (hi == gamma + 1) {
+    info.z = (int)leaf_start[gamma + 1];
+    info.w = (int)(leaf_start[gamma + 2] - leaf_start[gamma + 1]);
+    parent_leaf[gamma + 1] = (int)((i << 1) | 1);
+  } else {
+    info.z = (int)(gamma + 1);
+    info.w = 0;
+    parent_node[gamma + 1] = (int)((i << 1) | 1);
+  }
+  child_info[i] = info;
+  if (i == 0) parent_node[0] = -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bottom-up refit: one thread per leaf computes the leaf box and climbs; at every internal node the
+// first arriver stores its child's record and stops, the second one merges and continues.
+// A child's 32 B record (box + ref + count) is written with two 16-byte stores.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS) refit_kernel(const float4* __restrict__ pts,
+                                                        const uint32_t* __restrict__ leaf_start, uint32_t n_leaves,
+                                                        const int4* __restrict__ child_info,
+                                                        const int32_t* __restrict__ parent_leaf,
+                                                        const int32_t* __restrict__ parent_node,
+                                                        uint32_t* __restrict__ arrive, Node* nodes,
+                                                        float* __restrict__ scene_box) {
+  const uint32_t leaf = blockIdx.x * THREADS + threadIdx.x;
+  if (leaf >= n_leaves) return;
+  const uint32_t b = leaf_start[leaf], e = leaf_start[leaf + 1];
+  float3 lo = make_float3(INFINITY, INFINITY, INFINITY), hi = make_float3(-INFINITY, -INFINITY, -INFINITY);
+  for (uint32_t i = b; i < e; ++i) {
+    const float4 p = __ldg(&pts[i]);
+    lo.x = fminf(lo.x, p.x); lo.y = fminf(lo.y, p.y); lo.z = fminf(lo.z, p.z);
+    hi.x = fmaxf(hi.x, p.x); hi.y = fmaxf(hi.y, p.y); hi.z = fmaxf(hi.z, p.z);
+  }
+  int32_t link = parent_leaf[leaf];
+  for (;;) {
+    const int node = link >> 1, slot = link & 1;
+    const int4 info = child_info[node];
+    const int ref = slot ? info.z : info.x, cnt = slot ? info.w : info.y;
+    float4* rec = reinterpret_cast<float4*>(nodes + node) + 2 * slot;
+    __stcg(rec, make_float4(lo.x, lo.y, lo.z, __int_as_float(ref)));
+    __stcg(rec + 1, make_float4(hi.x, hi.y, hi.z, __int_as_float(cnt)));
+    __threadfence();
+    if (atomicAdd(&arrive[node], 1u) == 0u) return;
+    const float4* sib = reinterpret_cast<const float4*>(nodes + node) + 2 * (1 - slot);
+    const float4 slo = __ldcg(sib), shi = __ldcg(sib + 1);
+    lo.x = fminf(lo.x, slo.x); lo.y = fminf(lo.y, slo.y); lo.z = fminf(lo.z, slo.z);
+    hi.x = fmaxf(hi.x, shi.x); hi.y = fmaxf(hi.y, shi.y); hi.z = fmaxf(hi.z, shi.z);
+    if (node == 0) {
+      scene_box[0] = lo.x; scene_box[1] = lo.y; scene_box[2] = lo.z;
+      scene_box[3] = hi.x; scene_box[4] = hi.y; scene_box[5] = hi.z;
+      return;
+    }
+    link = parent_node[node];
+  }
+}
+
+}  // namespace lbvh
+}  // namespace tknn

@@ -1,0 +1,217 @@
+// radix_sort.cuh — hand-written onesweep LSD radix sort for (u64 key, u32 value) pairs.
+//
+// Replaces nothing the reference wrote itself: the sort is the first half of the LBVH builder that
+// stands in for optixAccelBuild (owl/UserGeomGroup.cpp:199-215).  One upfront histogram pass for
+// all 8 digits, then 8 scatter passes; each pass reads and writes every pair exactly once and
+// resolves the cross-tile digit offsets with decoupled look-back (single sweep), so the whole
+// sort moves 8 x 24 B per pair plus one 8 B histogram read.  Stable.
+#pragma once
+#include "common.cuh"
+
+namespace tknn {
+namespace rsort {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int PASSES = 64 / RADIX_BITS;
+constexpr int THREADS = 256;
+constexpr int WARPS = THREADS / 32;
+constexpr int ITEMS = 16;                   // pairs per thread
+constexpr int TILE = THREADS * ITEMS;       // 4096 pairs per tile
+constexpr uint32_t FLAG_AGG = 1u << 30;     // tile aggregate published
+constexpr uint32_t FLAG_PREFIX = 2u << 30;  // inclusive prefix published
+constexpr uint32_t FLAG_MASK = 3u << 30;
+constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
+constexpr uint64_t MAX_N = (1ull << 30) - 1;  // counts share a word with the two flag bits
+
+constexpr size_t DYN_SMEM = (size_t)TILE * (sizeof(uint64_t) + sizeof(uint32_t));
+
+__host__ __device__ inline uint32_t num_tiles(uint64_t n) { return (uint32_t)((n + TILE - 1) / TILE); }
+
+// hist[pass][digit] += count, all passes in one read of the keys.
+__global__ void __launch_bounds__(THREADS) histogram_kernel(const uint64_t* __restrict__ keys, uint64_t n,
+                                                            uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_hist[PASSES * RADIX];
+  for (int i = threadIdx.x; i < PASSES * RADIX; i += THREADS) s_hist[i] = 0;
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * THREADS;
+  for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride) {
+    const uint64_t key = keys[i];
+#pragma unroll
+    for (int p = 0; p < PASSES; ++p) atomicAdd(&s_hist[p * RADIX + (uint32_t)((key >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < PASSES * RADIX; i += THREADS) {
+    const uint32_t c = s_hist[i];
+    if (c) atomicAdd(&hist[i], c);
+  }
+}
+
+// in-place exclusive scan of each pass's 256 bins: one block per pass.
+__global__ void __launch_bounds__(RADIX) scan_histogram_kernel(uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_warp[RADIX / 32];
+  uint32_t* h = hist + blockIdx.x * RADIX;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t v = h[threadIdx.x];
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(FULL_MASK, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint32_t off = 0;
+  for (int w = 0; w < warp; ++w) off += s_warp[w];
+  h[threadIdx.x] = off + inc - v;
+}
+
+// One onesweep pass over digit `shift / 8`.
+__global__ void __launch_bounds__(THREADS)
+    onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                    uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint64_t n, int shift,
+                    const uint32_t* __restrict__ bin_offset, uint32_t* status, uint32_t* tile_counter) {
+  __shared__ uint32_t s_warp_hist[WARPS][RADIX];
+  __shared__ uint32_t s_digit_start[RADIX];
+  __shared__ uint32_t s_scatter[RADIX];
+  __shared__ uint32_t s_wsum[WARPS];
+  __shared__ uint32_t s_tile;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  uint64_t* s_keys = reinterpret_cast<uint64_t*>(s_dyn);
+  uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + TILE);
+
+  // dynamic tile ids: a tile only ever waits on tiles that started before it (deadlock freedom)
+  if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+  for (int i = threadIdx.x; i < WARPS * RADIX; i += THREADS) (&s_warp_hist[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint64_t base = (uint64_t)tile * TILE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  uint64_t key[ITEMS];
+  uint32_t val[ITEMS];
+  uint32_t rank[ITEMS];
+  const uint64_t wbase = base + (uint64_t)warp * (32 * ITEMS);
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint64_t idx = wbase + i * 32 + lane;
+    const bool ok = idx < n;
+    key[i] = ok ? keys_in[idx] : ~0ull;  // padding ranks after every real key of digit 255
+    val[i] = ok ? vals_in[idx] : 0u;
+  }
+  // warp-local stable ranking: lanes holding the same digit find each other with match.any; the
+  // lowest of them bumps the warp's digit counter for the whole peer group.
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint32_t d = (uint32_t)(key[i] >> shift) & (RADIX - 1);
+    const uint32_t peers = __match_any_sync(FULL_MASK, d);
+    const int leader = __ffs(peers) - 1;
+    uint32_t old = 0;
+    if (lane == leader) {
+      old = s_warp_hist[warp][d];
+      s_warp_hist[warp][d] = old + __popc(peers);
+    }
+    old = __shfl_sync(FULL_MASK, old, leader);
+    rank[i] = old + __popc(peers & lt_mask);
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // thread d owns digit d: exclusive scan of the warp counters, publish the tile aggregate
+  const int d = threadIdx.x;
+  uint32_t total = 0;
+#pragma unroll
+  for (int w = 0; w < WARPS; ++w) {
+    const uint32_t c = s_warp_hist[w][d];
+    s_warp_hist[w][d] = total;
+    total += c;
+  }
+  uint32_t* st = status + (size_t)tile * RADIX;
+  atomicExch(&st[d], total | (tile == 0 ? FLAG_PREFIX : FLAG_AGG));
+
+  // exclusive scan of `total` over the 256 digits -> where each digit starts inside the tile
+  uint32_t inc = total;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(FULL_MASK, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_wsum[warp] = inc;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (int w = 0; w < warp; ++w) woff += s_wsum[w];
+  const uint32_t dstart = woff + inc - total;
+  s_digit_start[d] = dstart;
+
+  // decoupled look-back over the preceding tiles for digit d
+  uint32_t excl = 0;
+  if (tile > 0) {
+    int64_t t = (int64_t)tile - 1;
+    for (;;) {
+      const volatile uint32_t* p = status + (size_t)t * RADIX + d;
+      uint32_t v;
+      do { v = *p; } while ((v & FLAG_MASK) == 0);
+      excl += v & VALUE_MASK;
+      if (v & FLAG_PREFIX) break;
+      --t;
+    }
+    atomicExch(&st[d], ((excl + total) & VALUE_MASK) | FLAG_PREFIX);
+  }
+  s_scatter[d] = bin_offset[d] + excl - dstart;  // global slot of tile-local position s is s_scatter[d] + s
+  __syncthreads();
+
+  // stage the tile in sorted order, then stream it out: runs of equal digits go to consecutive addresses
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint32_t dg = (uint32_t)(key[i] >> shift) & (RADIX - 1);
+    const uint32_t pos = s_digit_start[dg] + s_warp_hist[warp][dg] + rank[i];
+    s_keys[pos] = key[i];
+    s_vals[pos] = val[i];
+  }
+  __syncthreads();
+  const uint32_t tile_n = (uint32_t)((n - base) < (uint64_t)TILE ? (n - base) : (uint64_t)TILE);
+  for (uint32_t s = threadIdx.x; s < tile_n; s += THREADS) {
+    const uint64_t k = s_keys[s];
+    const uint32_t dg = (uint32_t)(k >> shift) & (RADIX - 1);
+    const uint32_t dst = s_scatter[dg] + s;
+    keys_out[dst] = k;
+    vals_out[dst] = s_vals[s];
+  }
+}
+
+// temp layout (uint32 words): hist[PASSES*RADIX] | counters[PASSES] (+pad to 16) | status[tiles*RADIX]
+inline size_t temp_words(uint64_t n) { return (size_t)PASSES * RADIX + 16 + (size_t)num_tiles(n) * RADIX; }
+
+// Sorts (keys_a, vals_a) using (keys_b, vals_b) as the alternate buffer; the result ends in the
+// `a` buffers (8 passes).  Returns the number of kernels launched.
+inline int sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint64_t n,
+                      uint32_t* temp, int sm_count, cudaStream_t stream) {
+  if (n == 0) return 0;
+  uint32_t* hist = temp;
+  uint32_t* counters = temp + PASSES * RADIX;
+  uint32_t* status = counters + 16;
+  const uint32_t tiles = num_tiles(n);
+  cudaMemsetAsync(temp, 0, sizeof(uint32_t) * (PASSES * RADIX + 16), stream);
+  cudaFuncSetAttribute(onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM);
+  uint64_t hb = (n + THREADS * 8 - 1) / (THREADS * 8);
+  const uint64_t hmax = (uint64_t)sm_count * 8;
+  if (hb > hmax) hb = hmax;
+  histogram_kernel<<<(unsigned)hb, THREADS, 0, stream>>>(keys_a, n, hist);
+  scan_histogram_kernel<<<PASSES, RADIX, 0, stream>>>(hist);
+  int launches = 2;
+  uint64_t *kin = keys_a, *kout = keys_b;
+  uint32_t *vin = vals_a, *vout = vals_b;
+  for (int p = 0; p < PASSES; ++p) {
+    cudaMemsetAsync(status, 0, sizeof(uint32_t) * (size_t)tiles * RADIX, stream);
+    onesweep_kernel<<<tiles, THREADS, DYN_SMEM, stream>>>(kin, vin, kout, vout, n, p * RADIX_BITS, hist + p * RADIX,
+                                                          status, counters + p);
+    ++launches;
+    uint64_t* tk = kin; kin = kout; kout = tk;
+    uint32_t* tv = vin; vin = vout; vout = tv;
+  }
+  return launches;
+}
+
+}  // namespace rsort
+}  // namespace tknn

@@ -1,0 +1,268 @@
+// traverse.cuh — the persistent, warp-cooperative LBVH traversal kernel.
+//
+// Replaces, in one kernel, the reference's raygen program (samples/s01-trueknn/deviceCode.cu:140-152),
+// the RT-core traversal behind optixTrace (owl/include/owl/owl_device.h:150-174) and the
+// intersection program with its global-memory sorted k-list (deviceCode.cu:62-138).
+//
+// Work unit = a GROUP of 32 consecutive queries in Morton order, one query per lane.  The warp
+// walks ONE stack for the group; a node is entered when ANY lane's exact point-to-box distance is
+// within that lane's own bound min(r^2, k-th best d2) (warp vote), so culling is per query, never
+// per group box.  A wanted leaf (<= 32 points, one coalesced 512 B float4 load) is staged in shared
+// memory and broadcast to all lanes: 32 queries x 32 points of distance tests per 512 B fetched.
+// Each lane owns a bounded max-heap of (d2, index) keys; candidates are filtered against the bound
+// into a bit mask first and inserted afterwards, so the divergent part only runs for real hits.
+//
+// Exactness: box distances use the same fmaf chain as point distances (monotone under RN), pruning
+// is strict (`>`), ties are resolved on the full (d2, index) key, self is excluded by index.
+#pragma once
+#include "common.cuh"
+
+namespace tknn {
+namespace trav {
+
+enum Mode { MODE_KNN = 0, MODE_RANGE_COUNT = 1 };
+
+struct Params {
+  const Node* nodes;
+  const float4* pts;         // sorted data points (x, y, z, original index bits)
+  const float4* queries;     // query points (x, y, z, row-id bits); == pts when all points are queries
+  const uint32_t* queue;     // optional list of query positions (rounds >= 2); nullptr = identity
+  const int32_t* self_ids;   // optional data index to exclude per query position; nullptr => see self_is_row
+  const float* query_r2;     // optional per-query-position squared radius cap
+  uint64_t n_active;         // queries in this launch
+  uint64_t q_begin;          // first query position when queue == nullptr
+  uint32_t n_groups;         // ceil(n_active / 32)
+  float r2;                  // squared search radius of this round (may be +inf)
+  int k;
+  int self_is_row;           // 1: exclude the data point whose index equals the query's row id
+  int row_mode;              // 0: output row = row id (scatter to build order); 1: row = position - q_begin;
+                             // 2: row = index inside this launch
+  int final_round;           // 1: emit every query, resolved or not (sentinels fill the rest)
+  int squared;               // 1: dist_out receives d2 instead of sqrtf(d2)
+  uint32_t* error;           // bit 0: traversal stack overflow (cannot happen for depth <= 95)
+  int32_t* idx_out;
+  float* dist_out;
+  int32_t* qid_out;          // row_mode 1: row id of each compact row (may be nullptr)
+  uint32_t* count_out;       // MODE_RANGE_COUNT
+  uint32_t* unresolved;      // one ballot word per group
+  uint32_t* group_counter;   // persistent-grid work counter
+  unsigned long long* counters;  // [0] node visits x active lanes, [1] point tests x active lanes, [2] inserts,
+                                 // [3] warp node loads, [4] warp leaf loads, [5] warp point loads
+};
+
+// ---- bounded max-heap of u64 keys in shared memory, slot s of lane l at H[s * 32 + l] ----------
+__device__ __forceinline__ void heap_push(uint64_t* H, int& cnt, uint64_t key) {
+  int i = cnt++;
+  while (i > 0) {
+    const int par = (i - 1) >> 1;
+    const uint64_t pk = H[par * 32];
+    if (pk >= key) break;
+    H[i * 32] = pk;
+    i = par;
+  }
+  H[i * 32] = key;
+}
+
+// place `key` at the root of a heap of `size` entries and sift it down
+__device__ __forceinline__ void heap_sift_root(uint64_t* H, int size, uint64_t key) {
+  int i = 0;
+  for (;;) {
+    int c = 2 * i + 1;
+    if (c >= size) break;
+    uint64_t ck = H[c * 32];
+    if (c + 1 < size) {
+      const uint64_t ck2 = H[(c + 1) * 32];
+      if (ck2 > ck) { ck = ck2; ++c; }
+    }
+    if (ck <= key) break;
+    H[i * 32] = ck;
+    i = c;
+  }
+  H[i * 32] = key;
+}
+
+__host__ __device__ inline size_t smem_per_warp(int k) {
+  return (size_t)k * 32 * sizeof(uint64_t) + 32 * sizeof(float4) + STACK_DEPTH * sizeof(int);
+}
+
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = P.k;
+  unsigned char* wbase = smem + (size_t)warp * smem_per_warp(MODE == MODE_KNN ? k : 0);
+  float4* stage = reinterpret_cast<float4*>(wbase);
+  int* stack = reinterpret_cast<int*>(wbase + 32 * sizeof(float4));
+  uint64_t* H = reinterpret_cast<uint64_t*>(wbase + 32 * sizeof(float4) + STACK_DEPTH * sizeof(int)) + lane;
+
+  unsigned long long c_nodes = 0, c_tests = 0, c_ins = 0, c_wnodes = 0, c_wleaves = 0, c_wpts = 0;
+
+  for (;;) {
+    uint32_t group = 0;
+    if (lane == 0) group = atomicAdd(P.group_counter, 1u);
+    group = __shfl_sync(FULL_MASK, group, 0);
+    if (group >= P.n_groups) break;
+
+    const uint64_t gi = (uint64_t)group * 32 + lane;
+    const bool valid = gi < P.n_active;
+    uint64_t qpos = 0;
+    if (valid) qpos = P.queue ? (uint64_t)P.queue[gi] : P.q_begin + gi;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) q = __ldg(&P.queries[qpos]);
+    const int row_id = __float_as_int(q.w);
+    int self = -1;
+    if (valid) self = P.self_ids ? P.self_ids[qpos] : (P.self_is_row ? row_id : -1);
+    float r2 = P.r2;
+    if (valid && P.query_r2) r2 = fminf(r2, P.query_r2[qpos]);
+    float bound = valid ? r2 : -1.0f;  // d2 >= 0 > -1: an idle lane never wants anything
+    int cnt = 0;
+
+    int sp = 0;
+    int node = 0;
+    for (;;) {
+      const float4* np = reinterpret_cast<const float4*>(P.nodes + node);
+      const float4 lo0 = __ldg(np), hi0 = __ldg(np + 1), lo1 = __ldg(np + 2), hi1 = __ldg(np + 3);
+      const float d0 = box_dist2(q.x, q.y, q.z, lo0, hi0);
+      const float d1 = box_dist2(q.x, q.y, q.z, lo1, hi1);
+      if (COUNT) { c_nodes += valid ? 1 : 0; c_wnodes += 1; }
+      const int ref0 = __float_as_int(lo0.w), cnt0 = __float_as_int(hi0.w);
+      const int ref1 = __float_as_int(lo1.w), cnt1 = __float_as_int(hi1.w);
+      // near-first among the two children, by majority of lanes
+      const unsigned closer1 = __ballot_sync(FULL_MASK, d1 < d0);
+      const unsigned closer0 = __ballot_sync(FULL_MASK, d0 < d1);
+      const bool swap = __popc(closer1) > __popc(closer0);
+
+      // ---- leaf children first (they tighten the bounds before anything is pushed) ----
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const bool second = (c == 1) != swap;  // false: child 0, true: child 1
+        const int lcount = second ? cnt1 : cnt0;
+        if (lcount <= 0) continue;
+        const float dc = second ? d1 : d0;
+        if (!__any_sync(FULL_MASK, dc <= bound)) continue;
+        const int start = second ? ref1 : ref0;
+        if (lane < lcount) stage[lane] = __ldg(&P.pts[(uint64_t)(uint32_t)start + lane]);
+        __syncwarp();
+        if (COUNT) { c_tests += valid ? lcount : 0; c_wleaves += 1; c_wpts += lcount; }
+        if (MODE == MODE_RANGE_COUNT) {
+          for (int j = 0; j < lcount; ++j) {
+            const float4 p = stage[j];
+            const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+            cnt += (d <= bound && __float_as_int(p.w) != self) ? 1 : 0;
+          }
+        } else {
+          uint32_t mask = 0;
+          for (int j = 0; j < lcount; ++j) {
+            const float4 p = stage[j];
+            const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+            mask |= (d <= bound ? 1u : 0u) << j;
+          }
+          while (__any_sync(FULL_MASK, mask != 0u)) {
+            if (mask) {
+              const int j = __ffs(mask) - 1;
+              mask &= mask - 1u;
+              const float4 p = stage[j];
+              const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+              const int pid = __float_as_int(p.w);
+              if (pid != self && d <= bound) {
+                const uint64_t key = make_key(d, pid);
+                if (cnt < k) {
+                  heap_push(H, cnt, key);
+                  if (cnt == k) bound = key_d2(H[0]);
+                  if (COUNT) c_ins += 1;
+                } else if (key < H[0]) {
+                  heap_sift_root(H, k, key);
+                  bound = key_d2(H[0]);
+                  if (COUNT) c_ins += 1;
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+
+      // ---- internal children, re-voted against the tightened bounds ----
+      const bool w0 = (cnt0 == 0) && (ref0 >= 0) && __any_sync(FULL_MASK, d0 <= bound);
+      const bool w1 = (cnt1 == 0) && (ref1 >= 0) && __any_sync(FULL_MASK, d1 <= bound);
+      if (w0 && w1) {
+        const int nearc = swap ? ref1 : ref0, farc = swap ? ref0 : ref1;
+        if (sp < STACK_DEPTH) {
+          if (lane == 0) stack[sp] = farc;
+          ++sp;
+        } else if (lane == 0) {
+          atomicOr(P.error, 1u);
+        }
+        node = nearc;
+      } else if (w0) {
+        node = ref0;
+      } else if (w1) {
+        node = ref1;
+      } else {
+        if (sp == 0) break;
+        --sp;
+        __syncwarp();
+        node = stack[sp];
+      }
+      __syncwarp();
+    }
+
+    // ---- emit ----
+    if (MODE == MODE_RANGE_COUNT) {
+      if (valid) P.count_out[row_id] = (uint32_t)cnt;
+    } else {
+      const bool resolved = valid && cnt == k;
+      const bool emit = valid && (resolved || P.final_round);
+      const unsigned un = __ballot_sync(FULL_MASK, valid && !resolved);
+      if (lane == 0 && P.unresolved) P.unresolved[group] = un;
+      if (emit) {
+        const uint64_t row = P.row_mode == 0 ? (uint64_t)(uint32_t)row_id : (P.row_mode == 1 ? qpos - P.q_begin : gi);
+        int32_t* io = P.idx_out + row * (uint64_t)k;
+        float* dd = P.dist_out + row * (uint64_t)k;
+        if (P.row_mode && P.qid_out) P.qid_out[row] = row_id;
+        for (int i = k - 1; i >= cnt; --i) { io[i] = -1; dd[i] = FLT_MAX; }
+        for (int i = cnt - 1; i >= 0; --i) {  // heap-sort extraction, largest first
+          const uint64_t top = H[0];
+          io[i] = key_idx(top);
+          dd[i] = P.squared ? key_d2(top) : __fsqrt_rn(key_d2(top));
+          if (i > 0) heap_sift_root(H, i, H[i * 32]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  if (COUNT && P.counters) {
+    atomicAdd(&P.counters[0], c_nodes);
+    atomicAdd(&P.counters[1], c_tests);
+    atomicAdd(&P.counters[2], c_ins);
+    if (lane == 0) {
+      atomicAdd(&P.counters[3], c_wnodes);
+      atomicAdd(&P.counters[4], c_wleaves);
+      atomicAdd(&P.counters[5], c_wpts);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Round compaction: unresolved ballot words -> the next round's queue, order preserved (so the
+// next round's groups are still Morton-coherent).  offsets[] = exclusive scan of popc(words).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) compact_queue_kernel(const uint32_t* __restrict__ words,
+                                                            const uint32_t* __restrict__ offsets, uint32_t n_groups,
+                                                            const uint32_t* __restrict__ queue_in, uint64_t q_begin,
+                                                            uint32_t* __restrict__ queue_out) {
+  const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  const uint32_t g = (uint32_t)(t >> 5);
+  if (g >= n_groups) return;
+  const int lane = (int)(t & 31);
+  const uint32_t w = words[g];
+  if ((w >> lane) & 1u) {
+    const uint32_t pos = offsets[g] + __popc(w & ((1u << lane) - 1u));
+    const uint64_t gi = (uint64_t)g * 32 + lane;
+    queue_out[pos] = queue_in ? queue_in[gi] : (uint32_t)(q_begin + gi);
+  }
+}
+
+}  // namespace trav
+}  // namespace tknn

@@ -1,0 +1,1091 @@
+// trueknn.cu — the C ABI of libtrueknn (include/trueknn.h) and the host-side round driver.
+//
+// Host logic replaced (reference file:line):
+//   tknn_build   <- hostCode.cpp:165-175,199-212  + owl/UserGeomGroup.cpp:39-241 + owl/UserGeom.cu:172-232
+//   tknn_search  <- hostCode.cpp:285-340 (round loop, termination scan, radius doubling, refits)
+//   error model  <- owl/helper/cuda.h:22-59 / owl/helper/optix.h:34-55 (throw / exit) -> return codes
+#include "../../include/trueknn.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "brute.cuh"
+#include "common.cuh"
+#include "lbvh.cuh"
+#include "radix_sort.cuh"
+#include "traverse.cuh"
+
+using namespace tknn;
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct tknn_ctx {
+  int device = 0;
+  int sm_count = 148;
+  size_t l2_bytes = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::string err;
+  // options
+  int leaf_size = 32, counters = 0, leaf_policy = 0, sample_groups = 128, blocks_per_sm = 0, squared = 0,
+      radius_quantile = 990;
+  // BVH
+  uint64_t n = 0;
+  uint32_t n_leaves = 0;
+  DevBuf pts, nodes, leaf_start;
+  float scene_box[6] = {0, 0, 0, 0, 0, 0};
+  // search scratch (grown on demand, kept across searches)
+  DevBuf queue_a, queue_b, unresolved, offsets, block_sums, scalars, stage_idx, stage_dist, sample;
+  cudaEvent_t ev[8] = {};
+  std::vector<cudaEvent_t> round_ev;
+  tknn_stats stats;
+  tknn_ctx() { std::memset(&stats, 0, sizeof(stats)); }
+};
+
+namespace {
+
+int fail(tknn_ctx* c, int code, const char* fmt, ...) {
+  if (c) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    c->err = buf;
+  }
+  return code;
+}
+
+#define TK_CUDA(c, expr)                                                                            \
+  do {                                                                                              \
+    cudaError_t e__ = (expr);                                                                       \
+    if (e__ != cudaSuccess) {                                                                       \
+      cudaGetLastError();                                                                           \
+      return fail((c), e__ == cudaErrorMemoryAllocation ? TKNN_ENOMEM : TKNN_ECUDA, "%s: %s (%s:%d)", #expr, \
+                  cudaGetErrorString(e__), __FILE__, __LINE__);                                     \
+    }                                                                                               \
+  } while (0)
+
+#define TK_TRY(expr)                 \
+  do {                               \
+    int rc__ = (expr);               \
+    if (rc__ != TKNN_OK) return rc__; \
+  } while (0)
+
+int ensure(tknn_ctx* c, DevBuf& b, size_t bytes) {
+  if (b.bytes >= bytes && b.p) return TKNN_OK;
+  if (b.p) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+  if (bytes == 0) bytes = 16;
+  TK_CUDA(c, cudaMalloc(&b.p, bytes));
+  b.bytes = bytes;
+  return TKNN_OK;
+}
+
+void release(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+}
+
+bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+struct ScopedDevice {
+  int prev = -1;
+  explicit ScopedDevice(int d) { cudaGetDevice(&prev); if (prev != d) cudaSetDevice(d); else prev = -1; }
+  ~ScopedDevice() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+inline unsigned blocks_for(uint64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// scalars layout (uint32 words unless noted)
+enum { SC_GROUP_COUNTER = 0, SC_TOTAL = 1, SC_ERROR = 2, SC_BOUNDS = 4 /* 7 words */, SC_SCENE = 12 /* 6 floats */,
+       SC_COUNTERS = 20 /* 6 x u64, 8-byte aligned */, SC_WORDS = 40 };
+
+// exclusive scan of popc(words[0..nw)) into offsets, total into scalars[SC_TOTAL]
+int popc_scan(tknn_ctx* c, const uint32_t* words, uint64_t nw, uint32_t* offsets, int* launches) {
+  const uint32_t nb = (uint32_t)((nw + lbvh::SCAN_CHUNK - 1) / lbvh::SCAN_CHUNK);
+  TK_TRY(ensure(c, c->block_sums, sizeof(uint32_t) * (size_t)(nb + 1)));
+  uint32_t* sums = c->block_sums.as<uint32_t>();
+  uint32_t* sc = c->scalars.as<uint32_t>();
+  lbvh::popc_reduce_kernel<<<nb, lbvh::THREADS, 0, c->stream>>>(words, nw, sums);
+  lbvh::scan_sums_kernel<<<1, lbvh::THREADS, 0, c->stream>>>(sums, nb, sc + SC_TOTAL);
+  lbvh::popc_apply_kernel<<<nb, lbvh::THREADS, 0, c->stream>>>(words, nw, sums, offsets);
+  if (launches) *launches += 3;
+  return TKNN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the round driver (shared by search / shard / query / estimator)
+// ---------------------------------------------------------------------------------------------
+struct Job {
+  const float4* queries = nullptr;
+  const int32_t* self_ids = nullptr;
+  const float* query_r2 = nullptr;
+  const uint32_t* first_queue = nullptr;  // optional explicit queue for round 1
+  uint64_t n_queries = 0;                 // queries in round 1
+  uint64_t q_begin = 0;
+  int self_is_row = 0;
+  int row_mode = 0;
+  int k = 0;
+  float start_radius = 0.f;  // > 0 or +inf
+  int squared = 0;
+  int32_t* idx_out = nullptr;
+  float* dist_out = nullptr;
+  int32_t* qid_out = nullptr;
+  bool record_stats = true;
+};
+
+template <int MODE>
+int launch_traverse(tknn_ctx* c, const trav::Params& P) {
+  const int k = MODE == trav::MODE_KNN ? P.k : 0;
+  const size_t per_warp = trav::smem_per_warp(k);
+  const size_t smem_cap = 200 * 1024;
+  int warps = (int)std::min<size_t>(8, smem_cap / per_warp);
+  if (warps < 1) return fail(c, TKNN_EINVAL, "k = %d needs %zu B of shared memory per warp", k, per_warp);
+  const size_t smem = per_warp * warps;
+  int bps = c->blocks_per_sm;
+  if (bps <= 0) {
+    bps = (int)std::min<size_t>(16, (220 * 1024) / (smem + 1024));
+    const int by_threads = 2048 / (warps * 32);
+    bps = std::max(1, std::min(bps, by_threads));
+  }
+  uint64_t grid = (uint64_t)c->sm_count * bps;
+  const uint64_t need = ((uint64_t)P.n_groups + warps - 1) / warps;
+  if (grid > need) grid = std::max<uint64_t>(1, need);
+  if (c->counters) {
+    auto kern = trav::traverse_kernel<MODE, true>;
+    TK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, warps * 32, smem, c->stream>>>(P);
+  } else {
+    auto kern = trav::traverse_kernel<MODE, false>;
+    TK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, warps * 32, smem, c->stream>>>(P);
+  }
+  TK_CUDA(c, cudaGetLastError());
+  return TKNN_OK;
+}
+
+int run_rounds(tknn_ctx* c, const Job& job, int* launches_io) {
+  uint32_t* sc = c->scalars.as<uint32_t>();
+  const uint64_t n0 = job.n_queries;
+  const uint32_t g0 = (uint32_t)((n0 + 31) / 32);
+  TK_TRY(ensure(c, c->unresolved, sizeof(uint32_t) * (size_t)(g0 + 1)));
+  TK_TRY(ensure(c, c->offsets, sizeof(uint32_t) * (size_t)(g0 + 1)));
+
+  const float diag = std::sqrt((c->scene_box[3] - c->scene_box[0]) * (c->scene_box[3] - c->scene_box[0]) +
+                               (c->scene_box[4] - c->scene_box[1]) * (c->scene_box[4] - c->scene_box[1]) +
+                               (c->scene_box[5] - c->scene_box[2]) * (c->scene_box[5] - c->scene_box[2]));
+  float radius = job.start_radius;
+  uint64_t active = n0;
+  const uint32_t* queue = job.first_queue;
+  int round = 0;
+  int launches = 0;
+  while (active > 0) {
+    const bool last = std::isinf(radius) || radius > 2.0f * diag || round >= TKNN_MAX_ROUNDS - 1;
+    trav::Params P;
+    std::memset(&P, 0, sizeof(P));
+    P.nodes = c->nodes.as<Node>();
+    P.pts = c->pts.as<float4>();
+    P.queries = job.queries;
+    P.queue = queue;
+    P.self_ids = job.self_ids;
+    P.query_r2 = job.query_r2;
+    P.n_active = active;
+    P.q_begin = job.q_begin;
+    P.n_groups = (uint32_t)((active + 31) / 32);
+    P.r2 = last ? INFINITY : radius * radius;
+    P.k = job.k;
+    P.self_is_row = job.self_is_row;
+    P.row_mode = job.row_mode;
+    P.final_round = last ? 1 : 0;
+    P.squared = job.squared;
+    P.error = sc + SC_ERROR;
+    P.idx_out = job.idx_out;
+    P.dist_out = job.dist_out;
+    P.qid_out = job.qid_out;
+    P.unresolved = last ? nullptr : c->unresolved.as<uint32_t>();
+    P.group_counter = sc + SC_GROUP_COUNTER;
+    P.counters = c->counters ? reinterpret_cast<unsigned long long*>(sc + SC_COUNTERS) : nullptr;
+
+    if (job.record_stats && round < TKNN_MAX_ROUNDS) {
+      if ((int)c->round_ev.size() < 2 * (round + 1)) {
+        cudaEvent_t a, b;
+        TK_CUDA(c, cudaEventCreate(&a));
+        TK_CUDA(c, cudaEventCreate(&b));
+        c->round_ev.push_back(a);
+        c->round_ev.push_back(b);
+      }
+      TK_CUDA(c, cudaEventRecord(c->round_ev[2 * round], c->stream));
+      c->stats.round_queries[round] = active;
+    }
+    TK_CUDA(c, cudaMemsetAsync(sc + SC_GROUP_COUNTER, 0, sizeof(uint32_t), c->stream));
+    TK_TRY(launch_traverse<trav::MODE_KNN>(c, P));
+    ++launches;
+
+    uint32_t next_active = 0;
+    if (!last) {
+      // order-preserving compaction of the unresolved queries (ballot words + prefix sums)
+      TK_TRY(popc_scan(c, c->unresolved.as<uint32_t>(), P.n_groups, c->offsets.as<uint32_t>(), &launches));
+      TK_CUDA(c, cudaMemcpyAsync(&next_active, sc + SC_TOTAL, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+      TK_CUDA(c, cudaStreamSynchronize(c->stream));  // the one host decision per round (hostCode.cpp:310-330)
+      if (next_active > 0) {
+        DevBuf& qout = (queue == c->queue_a.as<uint32_t>()) ? c->queue_b : c->queue_a;
+        TK_TRY(ensure(c, qout, sizeof(uint32_t) * (size_t)next_active));
+        trav::compact_queue_kernel<<<blocks_for((uint64_t)P.n_groups * 32, 256), 256, 0, c->stream>>>(
+            c->unresolved.as<uint32_t>(), c->offsets.as<uint32_t>(), P.n_groups, queue, job.q_begin, qout.as<uint32_t>());
+        ++launches;
+        queue = qout.as<uint32_t>();
+      }
+    }
+    if (job.record_stats && round < TKNN_MAX_ROUNDS) TK_CUDA(c, cudaEventRecord(c->round_ev[2 * round + 1], c->stream));
+    ++round;
+    active = next_active;
+    if (!last) radius *= 2.0f;
+  }
+  if (job.record_stats) {
+    c->stats.rounds = round;
+    c->stats.final_radius = round > 0 ? radius : job.start_radius;
+  }
+  if (launches_io) *launches_io += launches;
+  return TKNN_OK;
+}
+
+// Sampled k-th-neighbour distance -> start radius (role of Util/random_sample.py:5-32).
+int estimate_radius(tknn_ctx* c, const float4* queries, uint64_t q_begin, uint64_t nq, const int32_t* self_ids,
+                    int self_is_row, int k, float* out, int* launches) {
+  const uint64_t groups = (nq + 31) / 32;
+  const uint64_t sg = std::min<uint64_t>((uint64_t)std::max(1, c->sample_groups), groups);
+  std::vector<uint32_t> q;
+  q.reserve(sg * 32);
+  for (uint64_t s = 0; s < sg; ++s) {
+    const uint64_t g = (groups * s) / sg;
+    for (int l = 0; l < 32; ++l) {
+      const uint64_t pos = g * 32 + l;
+      if (pos < nq) q.push_back((uint32_t)(q_begin + pos));
+    }
+  }
+  const size_t m = q.size();
+  TK_TRY(ensure(c, c->sample, m * sizeof(uint32_t) + m * (size_t)k * (sizeof(int32_t) + sizeof(float))));
+  uint32_t* dq = c->sample.as<uint32_t>();
+  int32_t* di = reinterpret_cast<int32_t*>(dq + m);
+  float* dd = reinterpret_cast<float*>(di + m * (size_t)k);
+  TK_CUDA(c, cudaMemcpyAsync(dq, q.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  Job job;
+  job.queries = queries;
+  job.self_ids = self_ids;
+  job.first_queue = dq;
+  job.n_queries = m;
+  job.q_begin = q_begin;
+  job.self_is_row = self_is_row;
+  job.row_mode = 2;
+  job.k = k;
+  job.start_radius = INFINITY;
+  job.squared = 0;
+  job.idx_out = di;
+  job.dist_out = dd;
+  job.record_stats = false;
+  const int saved = c->counters;
+  c->counters = 0;
+  int rc = run_rounds(c, job, launches);
+  c->counters = saved;
+  TK_TRY(rc);
+  std::vector<float> h(m * (size_t)k);
+  TK_CUDA(c, cudaMemcpyAsync(h.data(), dd, h.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  TK_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::vector<float> kth(m);
+  for (size_t i = 0; i < m; ++i) kth[i] = h[i * k + (k - 1)];
+  size_t pos = (size_t)((double)(m - 1) * std::min(1000, std::max(0, c->radius_quantile)) / 1000.0);
+  std::nth_element(kth.begin(), kth.begin() + pos, kth.end());
+  float r = kth[pos];
+  if (!(r > 0.0f) || !std::isfinite(r)) {
+    // degenerate sample (duplicates): fall back to the largest finite positive value, else unbounded
+    r = 0.0f;
+    for (float v : kth) if (std::isfinite(v) && v > r) r = v;
+    if (!(r > 0.0f)) r = INFINITY;
+  }
+  *out = r;
+  return TKNN_OK;
+}
+
+int check_ctx(tknn_ctx* c) { return c ? TKNN_OK : TKNN_EINVAL; }
+
+int read_error_flag(tknn_ctx* c) {
+  uint32_t e = 0;
+  TK_CUDA(c, cudaMemcpyAsync(&e, c->scalars.as<uint32_t>() + SC_ERROR, sizeof(e), cudaMemcpyDeviceToHost, c->stream));
+  TK_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (e) return fail(c, TKNN_ECUDA, "traversal stack overflow (BVH deeper than %d)", STACK_DEPTH);
+  return TKNN_OK;
+}
+
+int collect_counters(tknn_ctx* c) {
+  if (!c->counters) return TKNN_OK;
+  unsigned long long h[6];
+  TK_CUDA(c, cudaMemcpyAsync(h, c->scalars.as<uint32_t>() + SC_COUNTERS, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  TK_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->stats.nodes_visited = h[0];
+  c->stats.points_tested = h[1];
+  c->stats.heap_inserts = h[2];
+  c->stats.warp_node_visits = h[3];
+  c->stats.warp_leaf_visits = h[4];
+  c->stats.warp_point_loads = h[5];
+  return TKNN_OK;
+}
+
+int finish_round_stats(tknn_ctx* c) {
+  for (int r = 0; r < c->stats.rounds && r < TKNN_MAX_ROUNDS; ++r) {
+    float ms = 0.f;
+    TK_CUDA(c, cudaEventElapsedTime(&ms, c->round_ev[2 * r], c->round_ev[2 * r + 1]));
+    c->stats.round_ms[r] = ms;
+  }
+  return TKNN_OK;
+}
+
+void reset_search_stats(tknn_ctx* c) {
+  tknn_stats& s = c->stats;
+  s.n_queries = 0; s.k = 0; s.rounds = 0; s.start_radius = s.final_radius = 0.f;
+  s.estimate_ms = s.search_ms = s.d2h_ms = 0.f;
+  std::memset(s.round_ms, 0, sizeof(s.round_ms));
+  std::memset(s.round_queries, 0, sizeof(s.round_queries));
+  s.kernel_launches = 0;
+  s.nodes_visited = s.points_tested = s.heap_inserts = 0;
+  s.warp_node_visits = s.warp_leaf_visits = s.warp_point_loads = 0;
+  s.d2h_bytes = 0;
+}
+
+// all-points search over query positions [q_begin, q_begin + nq) of the sorted order
+int search_range(tknn_ctx* c, int k, float start_radius, uint64_t q_begin, uint64_t nq, int row_mode, int32_t* qid_out,
+                 int32_t* idx_out, float* dist_out, uint64_t rows) {
+  if (c->n == 0) return fail(c, TKNN_ESTATE, "tknn_search before tknn_build");
+  if (k < 1 || k > TKNN_MAX_K) return fail(c, TKNN_EINVAL, "k = %d outside [1, %d]", k, TKNN_MAX_K);
+  if ((uint64_t)k > c->n - 1) return fail(c, TKNN_EINVAL, "k = %d > n - 1 = %llu: fewer than k neighbours exist", k,
+                                          (unsigned long long)(c->n - 1));
+  if (std::isnan(start_radius)) return fail(c, TKNN_EINVAL, "start_radius is NaN");
+  if (!idx_out || !dist_out) return fail(c, TKNN_EINVAL, "null output array");
+  reset_search_stats(c);
+  c->stats.n_queries = nq;
+  c->stats.k = k;
+  uint32_t* sc = c->scalars.as<uint32_t>();
+
+  const bool idx_dev = is_device_ptr(idx_out), dist_dev = is_device_ptr(dist_out);
+  const bool qid_dev = qid_out ? is_device_ptr(qid_out) : true;
+  int32_t* d_idx = idx_out;
+  float* d_dist = dist_out;
+  int32_t* d_qid = qid_out;
+  const size_t out_elems = (size_t)rows * (size_t)k;
+  if (!idx_dev || (qid_out && !qid_dev)) {
+    TK_TRY(ensure(c, c->stage_idx, out_elems * sizeof(int32_t) + (qid_out ? rows * sizeof(int32_t) : 0)));
+    if (!idx_dev) d_idx = c->stage_idx.as<int32_t>();
+    if (qid_out && !qid_dev) d_qid = c->stage_idx.as<int32_t>() + out_elems;
+  }
+  if (!dist_dev) {
+    TK_TRY(ensure(c, c->stage_dist, out_elems * sizeof(float)));
+    d_dist = c->stage_dist.as<float>();
+  }
+
+  TK_CUDA(c, cudaMemsetAsync(sc + SC_ERROR, 0, sizeof(uint32_t), c->stream));
+  TK_CUDA(c, cudaMemsetAsync(sc + SC_COUNTERS, 0, 6 * sizeof(unsigned long long), c->stream));
+  TK_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+  int launches = 0;
+  float r0 = start_radius;
+  if (nq > 0 && !(r0 > 0.0f)) {
+    TK_TRY(estimate_radius(c, c->pts.as<float4>(), q_begin, nq, nullptr, 1, k, &r0, &launches));
+  }
+  TK_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  c->stats.start_radius = r0;
+
+  Job job;
+  job.queries = c->pts.as<float4>();
+  job.n_queries = nq;
+  job.q_begin = q_begin;
+  job.self_is_row = 1;
+  job.row_mode = row_mode;
+  job.k = k;
+  job.start_radius = r0;
+  job.squared = c->squared;
+  job.idx_out = d_idx;
+  job.dist_out = d_dist;
+  job.qid_out = d_qid;
+  TK_TRY(run_rounds(c, job, &launches));
+  TK_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+
+  if (!idx_dev) {
+    TK_CUDA(c, cudaMemcpyAsync(idx_out, d_idx, out_elems * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    c->stats.d2h_bytes += out_elems * sizeof(int32_t);
+  }
+  if (!dist_dev) {
+    TK_CUDA(c, cudaMemcpyAsync(dist_out, d_dist, out_elems * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    c->stats.d2h_bytes += out_elems * sizeof(float);
+  }
+  if (qid_out && !qid_dev) {
+    TK_CUDA(c, cudaMemcpyAsync(qid_out, d_qid, rows * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    c->stats.d2h_bytes += rows * sizeof(int32_t);
+  }
+  TK_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+  TK_CUDA(c, cudaStreamSynchronize(c->stream));
+  TK_CUDA(c, cudaEventElapsedTime(&c->stats.estimate_ms, c->ev[0], c->ev[1]));
+  TK_CUDA(c, cudaEventElapsedTime(&c->stats.search_ms, c->ev[0], c->ev[2]));
+  TK_CUDA(c, cudaEventElapsedTime(&c->stats.d2h_ms, c->ev[2], c->ev[3]));
+  if (start_radius > 0.0f) c->stats.estimate_ms = 0.f;
+  c->stats.kernel_launches = (uint32_t)launches;
+  TK_TRY(finish_round_stats(c));
+  TK_TRY(collect_counters(c));
+  TK_TRY(read_error_flag(c));
+  return TKNN_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int tknn_version(void) { return TKNN_VERSION; }
+
+const char* tknn_last_error(const tknn_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int tknn_create(int device, tknn_ctx** out) {
+  if (!out) return TKNN_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) { cudaGetLastError(); return TKNN_ECUDA; }  // no CPU fallback
+  if (device < 0 || device >= count) return TKNN_EINVAL;
+  tknn_ctx* c = new (std::nothrow) tknn_ctx();
+  if (!c) return TKNN_ENOMEM;
+  c->device = device;
+  ScopedDevice sd(device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return TKNN_ECUDA; }
+  if (prop.major < 10) { delete c; return TKNN_ECUDA; }  // sm_100a code only
+  c->sm_count = prop.multiProcessorCount;
+  c->l2_bytes = (size_t)prop.l2CacheSize;
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return TKNN_ECUDA; }
+  c->stream = c->own_stream;
+  for (auto& ev : c->ev)
+    if (cudaEventCreate(&ev) != cudaSuccess) { delete c; return TKNN_ECUDA; }
+  if (cudaMalloc(&c->scalars.p, SC_WORDS * sizeof(uint32_t)) != cudaSuccess) { delete c; return TKNN_ENOMEM; }
+  c->scalars.bytes = SC_WORDS * sizeof(uint32_t);
+  *out = c;
+  return TKNN_OK;
+}
+
+int tknn_destroy(tknn_ctx* c) {
+  if (!c) return TKNN_EINVAL;
+  ScopedDevice sd(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (DevBuf* b : {&c->pts, &c->nodes, &c->leaf_start, &c->queue_a, &c->queue_b, &c->unresolved, &c->offsets,
+                    &c->block_sums, &c->scalars, &c->stage_idx, &c->stage_dist, &c->sample})
+    release(*b);
+  for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : c->round_ev) cudaEventDestroy(ev);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+  return TKNN_OK;
+}
+
+int tknn_set_stream(tknn_ctx* c, void* cuda_stream) {
+  TK_TRY(check_ctx(c));
+  c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+  return TKNN_OK;
+}
+
+int tknn_set_option(tknn_ctx* c, int key, int64_t value) {
+  TK_TRY(check_ctx(c));
+  switch (key) {
+    case TKNN_OPT_LEAF_SIZE:
+      if (value < 2 || value > MAX_LEAF) return fail(c, TKNN_EINVAL, "leaf size %lld outside [2, %d]", (long long)value, MAX_LEAF);
+      c->leaf_size = (int)value;
+      return TKNN_OK;
+    case TKNN_OPT_COUNTERS: c->counters = value ? 1 : 0; return TKNN_OK;
+    case TKNN_OPT_LEAF_POLICY:
+      if (value != 0 && value != 1) return fail(c, TKNN_EINVAL, "leaf policy must be 0 or 1");
+      c->leaf_policy = (int)value;
+      return TKNN_OK;
+    case TKNN_OPT_SAMPLE_GROUPS:
+      if (value < 1 || value > 65536) return fail(c, TKNN_EINVAL, "sample groups outside [1, 65536]");
+      c->sample_groups = (int)value;
+      return TKNN_OK;
+    case TKNN_OPT_BLOCKS_PER_SM:
+      if (value < 0 || value > 32) return fail(c, TKNN_EINVAL, "blocks per SM outside [0, 32]");
+      c->blocks_per_sm = (int)value;
+      return TKNN_OK;
+    case TKNN_OPT_SQUARED_DIST: c->squared = value ? 1 : 0; return TKNN_OK;
+    case TKNN_OPT_RADIUS_QUANTILE:
+      if (value < 0 || value > 1000) return fail(c, TKNN_EINVAL, "radius quantile outside [0, 1000] per mille");
+      c->radius_quantile = (int)value;
+      return TKNN_OK;
+    default: return fail(c, TKNN_EINVAL, "unknown option %d", key);
+  }
+}
+
+int tknn_build(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int stride_floats) {
+  TK_TRY(check_ctx(c));
+  if (!xyz) return fail(c, TKNN_EINVAL, "null point array");
+  if (dim != 2 && dim != 3) return fail(c, TKNN_EINVAL, "dim = %d (must be 2 or 3, hostCode.cpp:114-124)", dim);
+  if (stride_floats < dim) return fail(c, TKNN_EINVAL, "stride %d < dim %d", stride_floats, dim);
+  if (n < 2) return fail(c, TKNN_EINVAL, "need at least 2 points (got %llu)", (unsigned long long)n);
+  if (n > rsort::MAX_N) return fail(c, TKNN_EINVAL, "n = %llu exceeds %llu points per device", (unsigned long long)n,
+                                    (unsigned long long)rsort::MAX_N);
+  ScopedDevice sd(c->device);
+  cudaStream_t st = c->stream;
+  c->n = 0;
+  c->n_leaves = 0;
+  tknn_stats& S = c->stats;
+  std::memset(&S, 0, sizeof(S));
+  int launches = 0;
+
+  // ---- stage the input ----
+  DevBuf in_stage, keys_a, keys_b, vals_a, vals_b, sort_tmp, delta, ballots, leaf_key, child_info, parent_leaf, parent_node,
+      arrive;
+  auto cleanup = [&]() {
+    for (DevBuf* b : {&in_stage, &keys_a, &keys_b, &vals_a, &vals_b, &sort_tmp, &delta, &ballots, &leaf_key, &child_info,
+                      &parent_leaf, &parent_node, &arrive})
+      release(*b);
+  };
+#define TK_B(expr) do { int rc_ = (expr); if (rc_ != TKNN_OK) { cleanup(); return rc_; } } while (0)
+#define TK_BC(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cudaGetLastError(); cleanup(); \
+    return fail(c, e_ == cudaErrorMemoryAllocation ? TKNN_ENOMEM : TKNN_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); } } while (0)
+
+  TK_BC(cudaEventRecord(c->ev[0], st));
+  const float* d_xyz = xyz;
+  if (!is_device_ptr(xyz)) {
+    const size_t bytes = (size_t)n * stride_floats * sizeof(float);
+    TK_B(ensure(c, in_stage, bytes));
+    TK_BC(cudaMemcpyAsync(in_stage.p, xyz, bytes, cudaMemcpyHostToDevice, st));
+    d_xyz = in_stage.as<float>();
+    S.h2d_bytes = bytes;
+  }
+  TK_BC(cudaEventRecord(c->ev[1], st));
+
+  // ---- scene bounds ----
+  uint32_t* sc = c->scalars.as<uint32_t>();
+  const uint32_t binit[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
+  TK_BC(cudaMemcpyAsync(sc + SC_BOUNDS, binit, sizeof(binit), cudaMemcpyHostToDevice, st));
+  {
+    const unsigned nb = (unsigned)std::min<uint64_t>((uint64_t)c->sm_count * 8, blocks_for(n, lbvh::THREADS));
+    lbvh::bounds_kernel<<<nb, lbvh::THREADS, 0, st>>>(d_xyz, n, dim, stride_floats, sc + SC_BOUNDS);
+    ++launches;
+  }
+  TK_BC(cudaEventRecord(c->ev[2], st));
+
+  // ---- Morton codes ----
+  TK_B(ensure(c, keys_a, n * sizeof(uint64_t)));
+  TK_B(ensure(c, keys_b, n * sizeof(uint64_t)));
+  TK_B(ensure(c, vals_a, n * sizeof(uint32_t)));
+  TK_B(ensure(c, vals_b, n * sizeof(uint32_t)));
+  lbvh::morton_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, n, dim, stride_floats, sc + SC_BOUNDS,
+                                                                             keys_a.as<uint64_t>(), vals_a.as<uint32_t>());
+  ++launches;
+  TK_BC(cudaEventRecord(c->ev[3], st));
+
+  // ---- onesweep radix sort ----
+  TK_B(ensure(c, sort_tmp, rsort::temp_words(n) * sizeof(uint32_t)));
+  launches += rsort::sort_pairs(keys_a.as<uint64_t>(), vals_a.as<uint32_t>(), keys_b.as<uint64_t>(), vals_b.as<uint32_t>(), n,
+                                sort_tmp.as<uint32_t>(), c->sm_count, st);
+  TK_BC(cudaGetLastError());
+  TK_BC(cudaEventRecord(c->ev[4], st));
+
+  // ---- leaf cut + point gather ----
+  const uint64_t nw = (n + 31) / 32;
+  TK_B(ensure(c, delta, n));
+  TK_B(ensure(c, ballots, nw * sizeof(uint32_t)));
+  TK_B(ensure(c, c->offsets, (nw + 1) * sizeof(uint32_t)));
+  lbvh::delta_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(keys_a.as<uint64_t>(), n, delta.as<uint8_t>());
+  const uint64_t force_split = (n <= (uint64_t)c->leaf_size) ? n / 2 : 0;
+  lbvh::leaf_flag_kernel<<<blocks_for(nw * 32, lbvh::THREADS), lbvh::THREADS, 0, st>>>(
+      delta.as<uint8_t>(), n, c->leaf_size, c->leaf_policy, force_split, ballots.as<uint32_t>());
+  launches += 2;
+  TK_B(popc_scan(c, ballots.as<uint32_t>(), nw, c->offsets.as<uint32_t>(), &launches));
+  uint32_t m = 0;
+  uint32_t bad[1] = {0};
+  TK_BC(cudaMemcpyAsync(&m, sc + SC_TOTAL, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  TK_BC(cudaMemcpyAsync(bad, sc + SC_BOUNDS + 6, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  TK_BC(cudaStreamSynchronize(st));  // the leaf count sizes every later launch
+  if (bad[0]) { cleanup(); return fail(c, TKNN_EINVAL, "non-finite coordinate in the input points"); }
+  if (m < 2) { cleanup(); return fail(c, TKNN_ECUDA, "internal: leaf cut produced %u leaves", m); }
+  TK_B(ensure(c, c->leaf_start, (size_t)(m + 1) * sizeof(uint32_t)));
+  TK_B(ensure(c, leaf_key, (size_t)m * sizeof(uint64_t)));
+  TK_B(ensure(c, c->pts, n * sizeof(float4)));
+  lbvh::leaf_emit_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(
+      ballots.as<uint32_t>(), c->offsets.as<uint32_t>(), keys_a.as<uint64_t>(), n, m, c->leaf_start.as<uint32_t>(),
+      leaf_key.as<uint64_t>());
+  lbvh::gather_points_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, dim, stride_floats,
+                                                                                   vals_a.as<uint32_t>(), n, c->pts.as<float4>());
+  launches += 2;
+  TK_BC(cudaEventRecord(c->ev[5], st));
+
+  // ---- Karras hierarchy ----
+  TK_B(ensure(c, c->nodes, (size_t)(m - 1) * sizeof(Node)));
+  TK_B(ensure(c, child_info, (size_t)(m - 1) * sizeof(int4)));
+  TK_B(ensure(c, parent_leaf, (size_t)m * sizeof(int32_t)));
+  TK_B(ensure(c, parent_node, (size_t)m * sizeof(int32_t)));
+  TK_B(ensure(c, arrive, (size_t)m * sizeof(uint32_t)));
+  TK_BC(cudaMemsetAsync(arrive.p, 0, (size_t)m * sizeof(uint32_t), st));
+  lbvh::karras_kernel<<<blocks_for(m - 1, lbvh::THREADS), lbvh::THREADS, 0, st>>>(
+      leaf_key.as<uint64_t>(), c->leaf_start.as<uint32_t>(), m, child_info.as<int4>(), parent_leaf.as<int32_t>(),
+      parent_node.as<int32_t>());
+  ++launches;
+  TK_BC(cudaEventRecord(c->ev[6], st));
+
+  // ---- bottom-up refit ----
+  lbvh::refit_kernel<<<blocks_for(m, lbvh::THREADS), lbvh::THREADS, 0, st>>>(
+      c->pts.as<float4>(), c->leaf_start.as<uint32_t>(), m, child_info.as<int4>(), parent_leaf.as<int32_t>(),
+      parent_node.as<int32_t>(), arrive.as<uint32_t>(), c->nodes.as<Node>(), reinterpret_cast<float*>(sc + SC_SCENE));
+  ++launches;
+  TK_BC(cudaGetLastError());
+  TK_BC(cudaEventRecord(c->ev[7], st));
+  TK_BC(cudaMemcpyAsync(c->scene_box, sc + SC_SCENE, 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  TK_BC(cudaStreamSynchronize(st));
+  cleanup();
+#undef TK_B
+#undef TK_BC
+
+  TK_CUDA(c, cudaEventElapsedTime(&S.h2d_ms, c->ev[0], c->ev[1]));
+  TK_CUDA(c, cudaEventElapsedTime(&S.bounds_ms, c->ev[1], c->ev[2]));
+  TK_CUDA(c, cudaEventElapsedTime(&S.morton_ms, c->ev[2], c->ev[3]));
+  TK_CUDA(c, cudaEventElapsedTime(&S.sort_ms, c->ev[3], c->ev[4]));
+  TK_CUDA(c, cudaEventElapsedTime(&S.leaves_ms, c->ev[4], c->ev[5]));
+  TK_CUDA(c, cudaEventElapsedTime(&S.hierarchy_ms, c->ev[5], c->ev[6]));
+  TK_CUDA(c, cudaEventElapsedTime(&S.refit_ms, c->ev[6], c->ev[7]));
+  TK_CUDA(c, cudaEventElapsedTime(&S.build_ms, c->ev[1], c->ev[7]));
+  S.n_points = n;
+  S.n_leaves = m;
+  S.n_nodes = m - 1;
+  S.build_launches = (uint32_t)launches;
+  c->n = n;
+  c->n_leaves = m;
+  return TKNN_OK;
+}
+
+int tknn_search(tknn_ctx* c, int k, float start_radius, int32_t* idx_out, float* dist_out) {
+  TK_TRY(check_ctx(c));
+  ScopedDevice sd(c->device);
+  return search_range(c, k, start_radius, 0, c->n, 0, nullptr, idx_out, dist_out, c->n);
+}
+
+uint64_t tknn_shard_capacity(uint64_t n, int n_shards) {
+  if (n_shards < 1) return 0;
+  const uint64_t groups = (n + 31) / 32;
+  return ((groups + n_shards - 1) / n_shards + 1) * 32;
+}
+
+int tknn_search_shard(tknn_ctx* c, int k, float start_radius, int shard, int n_shards, int32_t* qid_out, int32_t* idx_out,
+                      float* dist_out, uint64_t* n_out) {
+  TK_TRY(check_ctx(c));
+  if (n_shards < 1 || shard < 0 || shard >= n_shards) return fail(c, TKNN_EINVAL, "shard %d of %d", shard, n_shards);
+  if (!n_out) return fail(c, TKNN_EINVAL, "null n_out");
+  ScopedDevice sd(c->device);
+  const uint64_t groups = (c->n + 31) / 32;
+  const uint64_t g0 = groups * (uint64_t)shard / (uint64_t)n_shards, g1 = groups * (uint64_t)(shard + 1) / (uint64_t)n_shards;
+  const uint64_t q0 = g0 * 32, q1 = std::min<uint64_t>(c->n, g1 * 32);
+  const uint64_t nq = q1 > q0 ? q1 - q0 : 0;
+  *n_out = nq;
+  if (nq == 0) {
+    if (c->n == 0) return fail(c, TKNN_ESTATE, "tknn_search_shard before tknn_build");
+    reset_search_stats(c);
+    return TKNN_OK;
+  }
+  return search_range(c, k, start_radius, q0, nq, 1, qid_out, idx_out, dist_out, nq);
+}
+
+int tknn_estimate_start_radius(tknn_ctx* c, int k, float* radius_out) {
+  TK_TRY(check_ctx(c));
+  if (!radius_out) return fail(c, TKNN_EINVAL, "null radius_out");
+  if (c->n == 0) return fail(c, TKNN_ESTATE, "tknn_estimate_start_radius before tknn_build");
+  if (k < 1 || k > TKNN_MAX_K || (uint64_t)k > c->n - 1) return fail(c, TKNN_EINVAL, "k = %d invalid for n = %llu", k,
+                                                                     (unsigned long long)c->n);
+  ScopedDevice sd(c->device);
+  int launches = 0;
+  return estimate_radius(c, c->pts.as<float4>(), 0, c->n, nullptr, 1, k, radius_out, &launches);
+}
+
+int tknn_query(tknn_ctx* c, const float* queries, uint64_t nq, int dim, int stride_floats, const int32_t* self_ids,
+               const float* init_radius, int k, float start_radius, int32_t* idx_out, float* dist_out) {
+  TK_TRY(check_ctx(c));
+  if (c->n == 0) return fail(c, TKNN_ESTATE, "tknn_query before tknn_build");
+  if (!queries && nq) return fail(c, TKNN_EINVAL, "null query array");
+  if (dim != 2 && dim != 3) return fail(c, TKNN_EINVAL, "dim = %d (must be 2 or 3)", dim);
+  if (stride_floats < dim) return fail(c, TKNN_EINVAL, "stride %d < dim %d", stride_floats, dim);
+  if (k < 1 || k > TKNN_MAX_K) return fail(c, TKNN_EINVAL, "k = %d outside [1, %d]", k, TKNN_MAX_K);
+  if ((uint64_t)k > c->n) return fail(c, TKNN_EINVAL, "k = %d > n = %llu", k, (unsigned long long)c->n);
+  if (nq > rsort::MAX_N) return fail(c, TKNN_EINVAL, "too many queries");
+  if (nq && (!idx_out || !dist_out)) return fail(c, TKNN_EINVAL, "null output array");
+  if (std::isnan(start_radius)) return fail(c, TKNN_EINVAL, "start_radius is NaN");
+  reset_search_stats(c);
+  c->stats.n_queries = nq;
+  c->stats.k = k;
+  if (nq == 0) return TKNN_OK;
+  ScopedDevice sd(c->device);
+  cudaStream_t st = c->stream;
+  uint32_t* sc = c->scalars.as<uint32_t>();
+
+  DevBuf q_stage, keys_a, keys_b, vals_a, vals_b, sort_tmp, qpts, sid_stage, sid_sorted, rad_stage, r2_sorted;
+  auto cleanup = [&]() {
+    for (DevBuf* b : {&q_stage, &keys_a, &keys_b, &vals_a, &vals_b, &sort_tmp, &qpts, &sid_stage, &sid_sorted, &rad_stage,
+                      &r2_sorted})
+      release(*b);
+  };
+#define TK_B(expr) do { int rc_ = (expr); if (rc_ != TKNN_OK) { cleanup(); return rc_; } } while (0)
+#define TK_BC(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cudaGetLastError(); cleanup(); \
+    return fail(c, e_ == cudaErrorMemoryAllocation ? TKNN_ENOMEM : TKNN_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); } } while (0)
+
+  TK_BC(cudaEventRecord(c->ev[0], st));
+  const float* d_q = queries;
+  if (!is_device_ptr(queries)) {
+    const size_t bytes = (size_t)nq * stride_floats * sizeof(float);
+    TK_B(ensure(c, q_stage, bytes));
+    TK_BC(cudaMemcpyAsync(q_stage.p, queries, bytes, cudaMemcpyHostToDevice, st));
+    d_q = q_stage.as<float>();
+  }
+  const int32_t* d_sid = self_ids;
+  if (self_ids && !is_device_ptr(self_ids)) {
+    TK_B(ensure(c, sid_stage, nq * sizeof(int32_t)));
+    TK_BC(cudaMemcpyAsync(sid_stage.p, self_ids, nq * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    d_sid = sid_stage.as<int32_t>();
+  }
+  const float* d_rad = init_radius;
+  if (init_radius && !is_device_ptr(init_radius)) {
+    TK_B(ensure(c, rad_stage, nq * sizeof(float)));
+    TK_BC(cudaMemcpyAsync(rad_stage.p, init_radius, nq * sizeof(float), cudaMemcpyHostToDevice, st));
+    d_rad = rad_stage.as<float>();
+  }
+  // Morton-sort the queries on the DATA's grid so that groups of 32 are spatially coherent
+  TK_B(ensure(c, keys_a, nq * sizeof(uint64_t)));
+  TK_B(ensure(c, keys_b, nq * sizeof(uint64_t)));
+  TK_B(ensure(c, vals_a, nq * sizeof(uint32_t)));
+  TK_B(ensure(c, vals_b, nq * sizeof(uint32_t)));
+  TK_B(ensure(c, sort_tmp, rsort::temp_words(nq) * sizeof(uint32_t)));
+  TK_B(ensure(c, qpts, nq * sizeof(float4)));
+  int launches = 0;
+  lbvh::morton_kernel<<<blocks_for(nq, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_q, nq, dim, stride_floats, sc + SC_BOUNDS,
+                                                                              keys_a.as<uint64_t>(), vals_a.as<uint32_t>());
+  ++launches;
+  launches += rsort::sort_pairs(keys_a.as<uint64_t>(), vals_a.as<uint32_t>(), keys_b.as<uint64_t>(), vals_b.as<uint32_t>(), nq,
+                                sort_tmp.as<uint32_t>(), c->sm_count, st);
+  lbvh::gather_points_kernel<<<blocks_for(nq, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_q, dim, stride_floats,
+                                                                                    vals_a.as<uint32_t>(), nq, qpts.as<float4>());
+  ++launches;
+  const int32_t* d_sid_sorted = nullptr;
+  const float* d_r2_sorted = nullptr;
+  if (d_sid) {
+    TK_B(ensure(c, sid_sorted, nq * sizeof(int32_t)));
+    brute::gather_i32_kernel<<<blocks_for(nq, 256), 256, 0, st>>>(d_sid, vals_a.as<uint32_t>(), nq, sid_sorted.as<int32_t>());
+    d_sid_sorted = sid_sorted.as<int32_t>();
+    ++launches;
+  }
+  if (d_rad) {
+    TK_B(ensure(c, r2_sorted, nq * sizeof(float)));
+    brute::gather_r2_kernel<<<blocks_for(nq, 256), 256, 0, st>>>(d_rad, vals_a.as<uint32_t>(), nq, r2_sorted.as<float>());
+    d_r2_sorted = r2_sorted.as<float>();
+    ++launches;
+  }
+
+  const bool idx_dev = is_device_ptr(idx_out), dist_dev = is_device_ptr(dist_out);
+  int32_t* d_idx = idx_out;
+  float* d_dist = dist_out;
+  const size_t out_elems = (size_t)nq * k;
+  if (!idx_dev) { TK_B(ensure(c, c->stage_idx, out_elems * sizeof(int32_t))); d_idx = c->stage_idx.as<int32_t>(); }
+  if (!dist_dev) { TK_B(ensure(c, c->stage_dist, out_elems * sizeof(float))); d_dist = c->stage_dist.as<float>(); }
+
+  TK_BC(cudaMemsetAsync(sc + SC_ERROR, 0, sizeof(uint32_t), st));
+  TK_BC(cudaMemsetAsync(sc + SC_COUNTERS, 0, 6 * sizeof(unsigned long long), st));
+  float r0 = start_radius;
+  // a query set can hold fewer than k reachable neighbours only through self exclusion / radius caps
+  const bool may_underfill = (uint64_t)k > c->n - (self_ids ? 1 : 0);
+  if (!(r0 > 0.0f)) {
+    if (init_radius || may_underfill) r0 = INFINITY;
+    else TK_B(estimate_radius(c, qpts.as<float4>(), 0, nq, d_sid_sorted, 0, k, &r0, &launches));
+  }
+  TK_BC(cudaEventRecord(c->ev[1], st));
+  c->stats.start_radius = r0;
+  Job job;
+  job.queries = qpts.as<float4>();
+  job.self_ids = d_sid_sorted;
+  job.query_r2 = d_r2_sorted;
+  job.n_queries = nq;
+  job.q_begin = 0;
+  job.self_is_row = 0;
+  job.row_mode = 0;
+  job.k = k;
+  job.start_radius = r0;
+  job.squared = c->squared;
+  job.idx_out = d_idx;
+  job.dist_out = d_dist;
+  TK_B(run_rounds(c, job, &launches));
+  TK_BC(cudaEventRecord(c->ev[2], st));
+  if (!idx_dev) { TK_BC(cudaMemcpyAsync(idx_out, d_idx, out_elems * sizeof(int32_t), cudaMemcpyDeviceToHost, st)); c->stats.d2h_bytes += out_elems * 4; }
+  if (!dist_dev) { TK_BC(cudaMemcpyAsync(dist_out, d_dist, out_elems * sizeof(float), cudaMemcpyDeviceToHost, st)); c->stats.d2h_bytes += out_elems * 4; }
+  TK_BC(cudaEventRecord(c->ev[3], st));
+  TK_BC(cudaStreamSynchronize(st));
+  cleanup();
+#undef TK_B
+#undef TK_BC
+  TK_CUDA(c, cudaEventElapsedTime(&c->stats.search_ms, c->ev[0], c->ev[2]));
+  TK_CUDA(c, cudaEventElapsedTime(&c->stats.d2h_ms, c->ev[2], c->ev[3]));
+  c->stats.kernel_launches = (uint32_t)launches;
+  TK_TRY(finish_round_stats(c));
+  TK_TRY(collect_counters(c));
+  TK_TRY(read_error_flag(c));
+  return TKNN_OK;
+}
+
+int tknn_range_count(tknn_ctx* c, float radius, uint32_t* count_out) {
+  TK_TRY(check_ctx(c));
+  if (c->n == 0) return fail(c, TKNN_ESTATE, "tknn_range_count before tknn_build");
+  if (!count_out) return fail(c, TKNN_EINVAL, "null output array");
+  if (!(radius >= 0.0f)) return fail(c, TKNN_EINVAL, "radius must be >= 0");
+  ScopedDevice sd(c->device);
+  reset_search_stats(c);
+  c->stats.n_queries = c->n;
+  uint32_t* sc = c->scalars.as<uint32_t>();
+  const bool dev = is_device_ptr(count_out);
+  uint32_t* d_out = count_out;
+  if (!dev) { TK_TRY(ensure(c, c->stage_idx, c->n * sizeof(uint32_t))); d_out = c->stage_idx.as<uint32_t>(); }
+  trav::Params P;
+  std::memset(&P, 0, sizeof(P));
+  P.nodes = c->nodes.as<Node>();
+  P.pts = c->pts.as<float4>();
+  P.queries = c->pts.as<float4>();
+  P.n_active = c->n;
+  P.n_groups = (uint32_t)((c->n + 31) / 32);
+  P.r2 = radius * radius;
+  P.k = 0;
+  P.self_is_row = 1;
+  P.final_round = 1;
+  P.error = sc + SC_ERROR;
+  P.count_out = d_out;
+  P.group_counter = sc + SC_GROUP_COUNTER;
+  P.counters = c->counters ? reinterpret_cast<unsigned long long*>(sc + SC_COUNTERS) : nullptr;
+  TK_CUDA(c, cudaMemsetAsync(sc + SC_ERROR, 0, sizeof(uint32_t), c->stream));
+  TK_CUDA(c, cudaMemsetAsync(sc + SC_COUNTERS, 0, 6 * sizeof(unsigned long long), c->stream));
+  TK_CUDA(c, cudaMemsetAsync(sc + SC_GROUP_COUNTER, 0, sizeof(uint32_t), c->stream));
+  TK_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+  TK_TRY(launch_traverse<trav::MODE_RANGE_COUNT>(c, P));
+  TK_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  if (!dev) {
+    TK_CUDA(c, cudaMemcpyAsync(count_out, d_out, c->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    c->stats.d2h_bytes = c->n * sizeof(uint32_t);
+  }
+  TK_CUDA(c, cudaStreamSynchronize(c->stream));
+  TK_CUDA(c, cudaEventElapsedTime(&c->stats.search_ms, c->ev[0], c->ev[2]));
+  c->stats.rounds = 1;
+  c->stats.kernel_launches = 1;
+  c->stats.start_radius = c->stats.final_radius = radius;
+  TK_TRY(collect_counters(c));
+  TK_TRY(read_error_flag(c));
+  return TKNN_OK;
+}
+
+int tknn_brute_force(tknn_ctx* c, const int32_t* query_ids, uint64_t nq, int k, int32_t* idx_out, float* dist_out) {
+  TK_TRY(check_ctx(c));
+  if (c->n == 0) return fail(c, TKNN_ESTATE, "tknn_brute_force before tknn_build");
+  if (k < 1 || k > TKNN_MAX_K || (uint64_t)k > c->n - 1) return fail(c, TKNN_EINVAL, "k = %d invalid for n = %llu", k,
+                                                                     (unsigned long long)c->n);
+  if (nq == 0) return TKNN_OK;
+  if (!query_ids || !idx_out || !dist_out) return fail(c, TKNN_EINVAL, "null array");
+  if (nq > (1u << 20)) return fail(c, TKNN_EINVAL, "at most 2^20 brute-force queries per call");
+  ScopedDevice sd(c->device);
+  cudaStream_t st = c->stream;
+  std::vector<int32_t> ids(nq);
+  if (is_device_ptr(query_ids)) {
+    TK_CUDA(c, cudaMemcpyAsync(ids.data(), query_ids, nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    TK_CUDA(c, cudaStreamSynchronize(st));
+  } else {
+    std::memcpy(ids.data(), query_ids, nq * sizeof(int32_t));
+  }
+  std::vector<uint32_t> perm(nq);
+  for (uint32_t i = 0; i < nq; ++i) perm[i] = i;
+  std::sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return ids[a] < ids[b]; });
+  std::vector<int32_t> sorted(nq);
+  for (uint32_t i = 0; i < nq; ++i) sorted[i] = ids[perm[i]];
+  for (uint32_t i = 0; i < nq; ++i) {
+    if (sorted[i] < 0 || (uint64_t)sorted[i] >= c->n) return fail(c, TKNN_EINVAL, "query id %d out of range", sorted[i]);
+    if (i && sorted[i] == sorted[i - 1]) return fail(c, TKNN_EINVAL, "duplicate query id %d", sorted[i]);
+  }
+  int splits = (int)std::max<uint64_t>(1, std::min<uint64_t>(256, ((uint64_t)c->sm_count * 16) / ((nq + 31) / 32)));
+  splits = (int)std::min<uint64_t>((uint64_t)splits, (c->n + 1023) / 1024);
+  DevBuf d_ids, d_perm, qpts, partial, o_idx, o_dist;
+  auto cleanup = [&]() { for (DevBuf* b : {&d_ids, &d_perm, &qpts, &partial, &o_idx, &o_dist}) release(*b); };
+#define TK_B(expr) do { int rc_ = (expr); if (rc_ != TKNN_OK) { cleanup(); return rc_; } } while (0)
+#define TK_BC(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cudaGetLastError(); cleanup(); \
+    return fail(c, e_ == cudaErrorMemoryAllocation ? TKNN_ENOMEM : TKNN_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); } } while (0)
+  TK_B(ensure(c, d_ids, nq * sizeof(int32_t)));
+  TK_B(ensure(c, d_perm, nq * sizeof(uint32_t)));
+  TK_B(ensure(c, qpts, nq * sizeof(float4)));
+  TK_B(ensure(c, partial, (size_t)splits * nq * k * sizeof(uint64_t)));
+  TK_BC(cudaMemcpyAsync(d_ids.p, sorted.data(), nq * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  TK_BC(cudaMemcpyAsync(d_perm.p, perm.data(), nq * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  const bool idx_dev = is_device_ptr(idx_out), dist_dev = is_device_ptr(dist_out);
+  int32_t* d_idx = idx_out;
+  float* d_dist = dist_out;
+  if (!idx_dev) { TK_B(ensure(c, o_idx, nq * k * sizeof(int32_t))); d_idx = o_idx.as<int32_t>(); }
+  if (!dist_dev) { TK_B(ensure(c, o_dist, nq * k * sizeof(float))); d_dist = o_dist.as<float>(); }
+  brute::lookup_queries_kernel<<<blocks_for(c->n, 256), 256, 0, st>>>(c->pts.as<float4>(), c->n, d_ids.as<int32_t>(),
+                                                                       (uint32_t)nq, qpts.as<float4>());
+  const size_t smem = 32 * sizeof(float4) + (size_t)k * 32 * sizeof(uint64_t);
+  TK_BC(cudaFuncSetAttribute(brute::brute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TK_BC(cudaFuncSetAttribute(brute::merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((nq + 31) / 32), (unsigned)splits);
+  brute::brute_kernel<<<grid, 32, smem, st>>>(c->pts.as<float4>(), c->n, qpts.as<float4>(), (uint32_t)nq, k, splits,
+                                              partial.as<uint64_t>());
+  brute::merge_keys_kernel<<<(unsigned)((nq + 31) / 32), 32, smem, st>>>(partial.as<uint64_t>(), splits, (uint32_t)nq, k,
+                                                                        d_perm.as<uint32_t>(), d_idx, d_dist);
+  TK_BC(cudaGetLastError());
+  if (!idx_dev) TK_BC(cudaMemcpyAsync(idx_out, d_idx, nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (!dist_dev) TK_BC(cudaMemcpyAsync(dist_out, d_dist, nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+  TK_BC(cudaStreamSynchronize(st));
+  cleanup();
+#undef TK_B
+#undef TK_BC
+  return TKNN_OK;
+}
+
+int tknn_merge_topk(tknn_ctx* c, const int32_t* idx_parts, const float* d2_parts, int parts, uint64_t nq, int k,
+                    int32_t* idx_out, float* dist_out) {
+  TK_TRY(check_ctx(c));
+  if (parts < 1 || k < 1 || k > TKNN_MAX_K) return fail(c, TKNN_EINVAL, "bad parts / k");
+  if (nq == 0) return TKNN_OK;
+  if (!idx_parts || !d2_parts || !idx_out || !dist_out) return fail(c, TKNN_EINVAL, "null array");
+  if (!is_device_ptr(idx_parts) || !is_device_ptr(d2_parts) || !is_device_ptr(idx_out) || !is_device_ptr(dist_out))
+    return fail(c, TKNN_EINVAL, "tknn_merge_topk takes device arrays");
+  ScopedDevice sd(c->device);
+  const size_t smem = (size_t)k * 32 * sizeof(uint64_t);
+  TK_CUDA(c, cudaFuncSetAttribute(brute::merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  brute::merge_lists_kernel<<<(unsigned)((nq + 31) / 32), 32, smem, c->stream>>>(idx_parts, d2_parts, parts, (uint32_t)nq, k,
+                                                                               idx_out, dist_out);
+  TK_CUDA(c, cudaGetLastError());
+  TK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return TKNN_OK;
+}
+
+int tknn_get_stats(const tknn_ctx* c, tknn_stats* out) {
+  if (!c || !out) return TKNN_EINVAL;
+  *out = c->stats;
+  return TKNN_OK;
+}
+
+int tknn_sort_pairs(tknn_ctx* c, uint64_t* keys, uint32_t* values, uint64_t n) {
+  TK_TRY(check_ctx(c));
+  if (n == 0) return TKNN_OK;
+  if (!keys || !values) return fail(c, TKNN_EINVAL, "null array");
+  if (n > rsort::MAX_N) return fail(c, TKNN_EINVAL, "n too large");
+  ScopedDevice sd(c->device);
+  cudaStream_t st = c->stream;
+  const bool kd = is_device_ptr(keys), vd = is_device_ptr(values);
+  DevBuf ka, kb, va, vb, tmp;
+  auto cleanup = [&]() { for (DevBuf* b : {&ka, &kb, &va, &vb, &tmp}) release(*b); };
+#define TK_B(expr) do { int rc_ = (expr); if (rc_ != TKNN_OK) { cleanup(); return rc_; } } while (0)
+#define TK_BC(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cudaGetLastError(); cleanup(); \
+    return fail(c, e_ == cudaErrorMemoryAllocation ? TKNN_ENOMEM : TKNN_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); } } while (0)
+  uint64_t* dk = keys;
+  uint32_t* dv = values;
+  if (!kd) { TK_B(ensure(c, ka, n * sizeof(uint64_t))); dk = ka.as<uint64_t>(); TK_BC(cudaMemcpyAsync(dk, keys, n * 8, cudaMemcpyHostToDevice, st)); }
+  if (!vd) { TK_B(ensure(c, va, n * sizeof(uint32_t))); dv = va.as<uint32_t>(); TK_BC(cudaMemcpyAsync(dv, values, n * 4, cudaMemcpyHostToDevice, st)); }
+  TK_B(ensure(c, kb, n * sizeof(uint64_t)));
+  TK_B(ensure(c, vb, n * sizeof(uint32_t)));
+  TK_B(ensure(c, tmp, rsort::temp_words(n) * sizeof(uint32_t)));
+  rsort::sort_pairs(dk, dv, kb.as<uint64_t>(), vb.as<uint32_t>(), n, tmp.as<uint32_t>(), c->sm_count, st);
+  TK_BC(cudaGetLastError());
+  if (!kd) TK_BC(cudaMemcpyAsync(keys, dk, n * 8, cudaMemcpyDeviceToHost, st));
+  if (!vd) TK_BC(cudaMemcpyAsync(values, dv, n * 4, cudaMemcpyDeviceToHost, st));
+  TK_BC(cudaStreamSynchronize(st));
+  cleanup();
+#undef TK_B
+#undef TK_BC
+  return TKNN_OK;
+}
+
+int tknn_get_bvh(const tknn_ctx* c, void* nodes_out, void* points_out, uint32_t* leaf_start_out) {
+  if (!c) return TKNN_EINVAL;
+  if (c->n == 0) return TKNN_ESTATE;
+  ScopedDevice sd(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (nodes_out && cudaMemcpy(nodes_out, c->nodes.p, (size_t)(c->n_leaves - 1) * sizeof(Node), cudaMemcpyDefault) != cudaSuccess)
+    return TKNN_ECUDA;
+  if (points_out && cudaMemcpy(points_out, c->pts.p, c->n * sizeof(float4), cudaMemcpyDefault) != cudaSuccess) return TKNN_ECUDA;
+  if (leaf_start_out &&
+      cudaMemcpy(leaf_start_out, c->leaf_start.p, (size_t)(c->n_leaves + 1) * sizeof(uint32_t), cudaMemcpyDefault) != cudaSuccess)
+    return TKNN_ECUDA;
+  return TKNN_OK;
+}
+
+int tknn_generate_uniform(tknn_ctx* c, uint64_t seed, uint64_t first, uint64_t n, float* xyz_out) {
+  TK_TRY(check_ctx(c));
+  if (n == 0) return TKNN_OK;
+  if (!xyz_out) return fail(c, TKNN_EINVAL, "null output array");
+  ScopedDevice sd(c->device);
+  const bool dev = is_device_ptr(xyz_out);
+  DevBuf tmp;
+  float* d = xyz_out;
+  if (!dev) {
+    int rc = ensure(c, tmp, 3 * n * sizeof(float));
+    if (rc != TKNN_OK) return rc;
+    d = tmp.as<float>();
+  }
+  brute::generate_uniform_kernel<<<blocks_for(3 * n, 256), 256, 0, c->stream>>>(seed, first, n, d);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && !dev) e = cudaMemcpyAsync(xyz_out, d, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  release(tmp);
+  if (e != cudaSuccess) return fail(c, TKNN_ECUDA, "generate_uniform: %s", cudaGetErrorString(e));
+  return TKNN_OK;
+}
+
+int tknn_measure_bandwidth(tknn_ctx* c, double* l2_gbs, double* hbm_gbs, int* sm_count, uint64_t* l2_bytes) {
+  TK_TRY(check_ctx(c));
+  ScopedDevice sd(c->device);
+  if (sm_count) *sm_count = c->sm_count;
+  if (l2_bytes) *l2_bytes = c->l2_bytes;
+  cudaStream_t st = c->stream;
+  DevBuf buf;
+  const size_t big = (size_t)2 << 30;  // HBM-sized: 2 GiB >> L2
+  int rc = ensure(c, buf, big);
+  if (rc != TKNN_OK) return rc;
+  cudaError_t e = cudaMemsetAsync(buf.p, 1, big, st);
+  uint32_t* sink = c->scalars.as<uint32_t>() + SC_WORDS - 1;
+  const unsigned grid = (unsigned)c->sm_count * 16;
+  float ms = 0.f;
+  auto run = [&](size_t bytes, int passes, double* out) {
+    const uint64_t words = bytes / 16;
+    brute::read_probe_kernel<<<grid, 256, 0, st>>>(buf.as<uint4>(), words, 1, sink);  // warm
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+      cudaEventRecord(c->ev[0], st);
+      brute::read_probe_kernel<<<grid, 256, 0, st>>>(buf.as<uint4>(), words, passes, sink);
+      cudaEventRecord(c->ev[1], st);
+      cudaEventSynchronize(c->ev[1]);
+      cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+      const double gbs = (double)bytes * passes / (ms * 1e-3) / 1e9;
+      if (gbs > best) best = gbs;
+    }
+    if (out) *out = best;
+  };
+  if (e == cudaSuccess) {
+    run((size_t)32 << 20, 64, l2_gbs);  // 32 MiB stays L2-resident
+    run(big, 1, hbm_gbs);
+    e = cudaGetLastError();
+  }
+  release(buf);
+  if (e != cudaSuccess) return fail(c, TKNN_ECUDA, "measure_bandwidth: %s", cudaGetErrorString(e));
+  return TKNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,323 @@
+"""Host-side mirror of the reference's TrueKNN sample interface over the libtrueknn C ABI.
+
+The reference has no library API for kNN — its interface is the command line of
+samples/s01-trueknn (hostCode.cpp:66-73: file, n, dim, start radius, k, out file) and the in-memory
+`Neigh` buffer (GeomTypes.h:22-28, read at hostCode.cpp:294).  `run_sample()` below keeps those six
+positional arguments; `TrueKNN` is the object behind it.  Every array argument may be a numpy array
+(host memory, staged inside the C call) or a CUDA `torch.Tensor` (device memory, zero-copy).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+import time
+
+import numpy as np
+
+from . import _lib
+from ._lib import Stats
+
+
+class TrueKNNError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{_lib.ERROR_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+def _is_tensor(a) -> bool:
+    return hasattr(a, "data_ptr") and hasattr(a, "is_cuda")
+
+
+def _ptr(a):
+    """Raw address of a numpy array or torch tensor (None -> NULL)."""
+    if a is None:
+        return None
+    if _is_tensor(a):
+        if not a.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return C.c_void_p(a.data_ptr())
+    if not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("array must be C-contiguous")
+    return C.c_void_p(a.ctypes.data)
+
+
+def _check_dtype(a, np_dtype, name):
+    if _is_tensor(a):
+        import torch
+
+        want = {np.float32: torch.float32, np.int32: torch.int32, np.uint32: torch.int32, np.uint64: torch.int64}[np_dtype]
+        if a.dtype != want and not (np_dtype is np.uint32 and a.dtype == torch.uint32):
+            raise TypeError(f"{name}: expected {want}, got {a.dtype}")
+    elif a.dtype != np_dtype:
+        raise TypeError(f"{name}: expected {np.dtype(np_dtype)}, got {a.dtype}")
+
+
+class TrueKNN:
+    """One LBVH + traversal context on one CUDA device (`tknn_ctx`)."""
+
+    def __init__(self, device: int = 0, **options):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        rc = self._L.tknn_create(int(device), C.byref(h))
+        if rc != _lib.OK:
+            raise TrueKNNError(rc, f"tknn_create(device={device}) failed — a CUDA sm_100 device is required, "
+                                   "there is no CPU fallback")
+        self._h = h
+        self.device = int(device)
+        self.n = 0
+        self._keep = None
+        for k, v in options.items():
+            self.set_option(k, v)
+
+    # ---- plumbing ----
+    def _check(self, rc: int):
+        if rc != _lib.OK:
+            raise TrueKNNError(rc, self._L.tknn_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.tknn_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    _OPTS = {
+        "leaf_size": _lib.OPT_LEAF_SIZE, "counters": _lib.OPT_COUNTERS, "leaf_policy": _lib.OPT_LEAF_POLICY,
+        "sample_groups": _lib.OPT_SAMPLE_GROUPS, "blocks_per_sm": _lib.OPT_BLOCKS_PER_SM,
+        "squared_dist": _lib.OPT_SQUARED_DIST, "radius_quantile": _lib.OPT_RADIUS_QUANTILE,
+    }
+
+    def set_option(self, name: str, value: int):
+        if name not in self._OPTS:
+            raise KeyError(name)
+        self._check(self._L.tknn_set_option(self._h, self._OPTS[name], int(value)))
+
+    def set_stream(self, cuda_stream: int | None):
+        """Run on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._check(self._L.tknn_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self._L.tknn_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def _out(self, like, rows, k, dtype):
+        if _is_tensor(like):
+            import torch
+
+            return torch.empty((rows, k), dtype={np.int32: torch.int32, np.float32: torch.float32}[dtype], device=like.device)
+        return np.empty((rows, k), dtype)
+
+    # ---- the path ----
+    def build(self, points, dim: int | None = None):
+        """Build the LBVH over `points` ([n, 2|3] float32; extra columns are skipped through the stride)."""
+        if not _is_tensor(points):
+            points = np.ascontiguousarray(points, dtype=np.float32)
+        _check_dtype(points, np.float32, "points")
+        if points.ndim != 2:
+            raise ValueError("points must be [n, >=dim]")
+        stride = int(points.shape[1])
+        if dim is None:
+            dim = min(stride, 3)
+        self._check(self._L.tknn_build(self._h, _ptr(points), int(points.shape[0]), int(dim), stride))
+        self.n = int(points.shape[0])
+        self._like = points
+        return self
+
+    def search(self, k: int, start_radius: float = 0.0, out=None):
+        """All-points kNN. Returns (idx [n,k] int32, dist [n,k] float32), rows in build order."""
+        if out is None:
+            idx = self._out(self._like, self.n, k, np.int32)
+            dist = self._out(self._like, self.n, k, np.float32)
+        else:
+            idx, dist = out
+        _check_dtype(idx, np.int32, "idx_out")
+        _check_dtype(dist, np.float32, "dist_out")
+        self._check(self._L.tknn_search(self._h, int(k), C.c_float(start_radius), _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+    def shard_capacity(self, n_shards: int) -> int:
+        return int(self._L.tknn_shard_capacity(self.n, int(n_shards)))
+
+    def search_shard(self, k: int, shard: int, n_shards: int, start_radius: float = 0.0, out=None):
+        """Query-sharded search: returns (qid [m], idx [m,k], dist [m,k]) for this shard's Morton slice."""
+        cap = self.shard_capacity(n_shards)
+        if out is None:
+            if _is_tensor(self._like):
+                import torch
+
+                qid = torch.empty((cap,), dtype=torch.int32, device=self._like.device)
+            else:
+                qid = np.empty((cap,), np.int32)
+            idx = self._out(self._like, cap, k, np.int32)
+            dist = self._out(self._like, cap, k, np.float32)
+        else:
+            qid, idx, dist = out
+        m = C.c_uint64(0)
+        self._check(self._L.tknn_search_shard(self._h, int(k), C.c_float(start_radius), int(shard), int(n_shards), _ptr(qid),
+                                              _ptr(idx), _ptr(dist), C.byref(m)))
+        m = int(m.value)
+        return qid[:m], idx[:m], dist[:m]
+
+    def query(self, queries, k: int, self_ids=None, init_radius=None, start_radius: float = 0.0, dim: int | None = None):
+        """kNN of a separate query set against the built BVH; rows follow the query order."""
+        if not _is_tensor(queries):
+            queries = np.ascontiguousarray(queries, dtype=np.float32)
+        _check_dtype(queries, np.float32, "queries")
+        nq, stride = int(queries.shape[0]), int(queries.shape[1])
+        if dim is None:
+            dim = min(stride, 3)
+        if self_ids is not None and not _is_tensor(self_ids):
+            self_ids = np.ascontiguousarray(self_ids, dtype=np.int32)
+        if init_radius is not None and not _is_tensor(init_radius):
+            init_radius = np.ascontiguousarray(init_radius, dtype=np.float32)
+        idx = self._out(queries, nq, k, np.int32)
+        dist = self._out(queries, nq, k, np.float32)
+        self._check(self._L.tknn_query(self._h, _ptr(queries), nq, int(dim), stride, _ptr(self_ids), _ptr(init_radius), int(k),
+                                       C.c_float(start_radius), _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+    def range_count(self, radius: float):
+        """Neighbours within the closed ball of `radius` for every point (DBSCAN core-point test)."""
+        if _is_tensor(self._like):
+            import torch
+
+            out = torch.empty((self.n,), dtype=torch.int32, device=self._like.device)
+        else:
+            out = np.empty((self.n,), np.uint32)
+        self._check(self._L.tknn_range_count(self._h, C.c_float(radius), _ptr(out)))
+        return out
+
+    def estimate_start_radius(self, k: int) -> float:
+        r = C.c_float(0)
+        self._check(self._L.tknn_estimate_start_radius(self._h, int(k), C.byref(r)))
+        return float(r.value)
+
+    def brute_force(self, query_ids, k: int):
+        """Exact tiled brute force on the GPU for selected data indices (second oracle)."""
+        if not _is_tensor(query_ids):
+            query_ids = np.ascontiguousarray(query_ids, dtype=np.int32)
+        nq = int(query_ids.shape[0])
+        idx = self._out(query_ids, nq, k, np.int32)
+        dist = self._out(query_ids, nq, k, np.float32)
+        self._check(self._L.tknn_brute_force(self._h, _ptr(query_ids), nq, int(k), _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+    def merge_topk(self, idx_parts, d2_parts):
+        """Merge [parts, nq, k] (idx, d2) device lists on (d2, index); returns (idx, dist=sqrt(d2))."""
+        parts, nq, k = (int(x) for x in idx_parts.shape)
+        idx = self._out(idx_parts, nq, k, np.int32)
+        dist = self._out(idx_parts, nq, k, np.float32)
+        self._check(self._L.tknn_merge_topk(self._h, _ptr(idx_parts), _ptr(d2_parts), parts, nq, k, _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+    # ---- introspection (tests / bench) ----
+    def sort_pairs(self, keys, values):
+        n = int(keys.shape[0])
+        self._check(self._L.tknn_sort_pairs(self._h, _ptr(keys), _ptr(values), n))
+        return keys, values
+
+    def get_bvh(self):
+        """Host copies: nodes [n_nodes,16] float32 (bit views for refs), points [n,4] float32, leaf_start [n_leaves+1]."""
+        st = self.stats()
+        nodes = np.empty((st["n_nodes"], 16), np.float32)
+        pts = np.empty((self.n, 4), np.float32)
+        leaf_start = np.empty((st["n_leaves"] + 1,), np.uint32)
+        self._check(self._L.tknn_get_bvh(self._h, _ptr(nodes), _ptr(pts), _ptr(leaf_start)))
+        return nodes, pts, leaf_start
+
+    def generate_uniform(self, seed: int, first: int, n: int, out=None):
+        if out is None:
+            out = np.empty((n, 3), np.float32)
+        self._check(self._L.tknn_generate_uniform(self._h, int(seed), int(first), int(n), _ptr(out)))
+        return out
+
+    def measure_bandwidth(self) -> dict:
+        l2, hbm, sms, l2b = C.c_double(0), C.c_double(0), C.c_int(0), C.c_uint64(0)
+        self._check(self._L.tknn_measure_bandwidth(self._h, C.byref(l2), C.byref(hbm), C.byref(sms), C.byref(l2b)))
+        return {"l2_gbs": l2.value, "hbm_read_gbs": hbm.value, "sm_count": sms.value, "l2_bytes": int(l2b.value)}
+
+
+# ------------------------------------------------------------------------------------------------
+# The sample's command line (hostCode.cpp:66-73) as a function.
+# ------------------------------------------------------------------------------------------------
+_FLOAT_RE = re.compile(r"[+-]?(?:\d+\.?\d*|\.\d+)(?:[eE][+-]?\d+)?")
+
+
+def read_points(path: str, n: int, dim: int) -> np.ndarray:
+    """Point-file grammar of the sample (hostCode.cpp:83-124): floats separated by ',' and/or blanks,
+    lines read while n*dim floats are still owed (the last line read is consumed whole), then chunked
+    by `dim`; dim 2 gives z = 0.  Fast path: a `.f32` file is raw little-endian float32 rows of `dim`."""
+    if dim not in (2, 3):
+        raise ValueError("dimension must be 2 or 3 (hostCode.cpp:114-124 creates no points otherwise)")
+    if path.endswith(".f32"):
+        flat = np.fromfile(path, dtype="<f4", count=n * dim)
+    else:
+        vals: list[float] = []
+        owed = n * dim
+        with open(path, "rb") as f:
+            for line in f:
+                if owed <= 0:
+                    break
+                # operator>> stops at the first token that is not a float; a ',' after a float is skipped
+                pos, text = 0, line.decode("latin-1")
+                ln = len(text)
+                while True:
+                    while pos < ln and text[pos].isspace():
+                        pos += 1
+                    if pos >= ln:
+                        break
+                    m = _FLOAT_RE.match(text, pos)
+                    if not m:
+                        break
+                    vals.append(float(m.group(0)))
+                    owed -= 1
+                    pos = m.end()
+                    if pos < ln and text[pos] == ",":
+                        pos += 1
+        flat = np.asarray(vals, dtype=np.float32)
+    if flat.size % dim:
+        raise ValueError(f"{flat.size} floats is not a multiple of dim={dim} (the reference throws std::out_of_range)")
+    pts = flat.reshape(-1, dim)
+    if dim == 2:
+        pts = np.concatenate([pts, np.zeros((pts.shape[0], 1), np.float32)], axis=1)
+    return np.ascontiguousarray(pts, dtype=np.float32)
+
+
+def run_sample(argv: list[str], device: int = 0, neighbours_path: str | None = None) -> dict:
+    """`sample01-trueknn file n dim start_radius k outfile` (samples/s01-trueknn/README.md:7-14).
+
+    Appends the total seconds (build + kNN) to `outfile` exactly like hostCode.cpp:346-356, and —
+    what the reference leaves commented out at hostCode.cpp:312-319 — optionally writes the
+    neighbours as `query,neighbourIndex,distance` lines to `neighbours_path`."""
+    if len(argv) != 6:
+        raise SystemExit("usage: trueknn <file> <n> <dim> <start radius> <k> <output file>")
+    path, n, dim, r0, k, outfile = argv[0], int(argv[1]), int(argv[2]), float(argv[3]), int(argv[4]), argv[5]
+    pts = read_points(path, n, dim)
+    with TrueKNN(device) as t:
+        t0 = time.perf_counter()
+        t.build(pts, dim=3)
+        t1 = time.perf_counter()
+        idx, dist = t.search(k, r0)
+        t2 = time.perf_counter()
+        st = t.stats()
+    total = (t1 - t0) + (t2 - t1)
+    with open(outfile, "a") as f:
+        f.write(f"{total}\n")
+    if neighbours_path:
+        q = np.repeat(np.arange(idx.shape[0]), k)
+        with open(neighbours_path, "w") as f:
+            for a, b, d in zip(q, idx.reshape(-1), dist.reshape(-1)):
+                f.write(f"{a},{b},{d:.9g}\n")
+    return {"build_s": t1 - t0, "knn_s": t2 - t1, "total_s": total, "rounds": st["rounds"], "idx": idx, "dist": dist,
+            "stats": st}

@@ -1,0 +1,31 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    """The CPU oracle (oracle/liboracle.so), built on demand. Test infrastructure only."""
+    from oracle import oracle as O
+
+    O.build()
+    return O
+
+
+@pytest.fixture()
+def knn():
+    """A fresh TrueKNN context on cuda:0. Fails loudly (no skip) when the extension or a GPU is missing."""
+    from owlraytracing_b200 import TrueKNN
+
+    t = TrueKNN(0)
+    yield t
+    t.close()

@@ -1,0 +1,255 @@
+"""GPU parity: the CUDA path through the C ABI vs the CPU oracle, bit-exact on indices."""
+import numpy as np
+import pytest
+
+from helpers import assert_knn_equal, rows_sorted
+from owlraytracing_b200 import TrueKNNError, datasets
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cfg1_100k_uniform_k5(knn, oracle):
+    """BASELINE.json configs[0]: 100K uniform, k=5, every query vs the host oracle."""
+    x = datasets.uniform(100_000, seed=42)
+    idx, dist = knn.build(x).search(5)
+    ref_idx, ref_dist = oracle.knn_kdtree(x, 5)
+    assert_knn_equal(idx, dist, ref_idx, ref_dist, "cfg1")
+    st = knn.stats()
+    assert st["rounds"] >= 1 and st["n_queries"] == 100_000
+    # brute force on a subset pins the kd-tree oracle itself at this size
+    sub = np.arange(0, 100_000, 97, dtype=np.int32)
+    bi, bd = oracle.knn_brute_queries(x, x[sub], 5, self_ids=sub)
+    assert (bi == ref_idx[sub]).all() and (bd == ref_dist[sub]).all()
+
+
+@pytest.mark.parametrize("k", [1, 2, 7, 10, 16, 33, 64])
+def test_uniform_various_k(knn, oracle, k):
+    x = datasets.uniform(30_000, seed=3)
+    idx, dist = knn.build(x).search(k)
+    ref = oracle.knn_kdtree(x, k)
+    assert_knn_equal(idx, dist, *ref, f"k={k}")
+    assert rows_sorted(dist)
+
+
+@pytest.mark.parametrize("m,k", [(6, 6), (7, 18), (8, 26), (5, 7)])
+def test_lattice_known_answers(knn, oracle, m, k):
+    """Unit lattice: shells at distance 1 (6), sqrt2 (12), sqrt3 (8): every shell is an index tie set."""
+    x = datasets.lattice(m)
+    idx, dist = knn.build(x).search(k)
+    ref = oracle.knn_brute(x, k)
+    assert_knn_equal(idx, dist, *ref, f"lattice {m}^3 k={k}")
+    centre = (m // 2) * (m * m + m + 1)
+    if m >= 5 and k >= 6:
+        assert (dist[centre][:6] == 1.0).all()
+        # lowest-index tie-break: the six unit neighbours appear in ascending index order
+        assert (np.diff(idx[centre][:6]) > 0).all()
+
+
+def test_duplicates_and_coincident_points(knn, oracle):
+    rng = np.random.default_rng(5)
+    base = rng.random((3000, 3), dtype=np.float32)
+    x = np.concatenate([base, base[:1500], base[:700], np.tile(base[:1], (200, 1))]).astype(np.float32)
+    for k in (3, 10, 40):
+        idx, dist = knn.build(x).search(k)
+        assert_knn_equal(idx, dist, *oracle.knn_brute(x, k), f"duplicates k={k}")
+    # self is excluded by INDEX, so a duplicate is a legal neighbour at distance 0 (deviceCode.cu:103)
+    assert dist[0][0] == 0.0 and idx[0][0] != 0
+
+
+def test_all_points_identical(knn, oracle):
+    x = np.full((500, 3), 0.25, np.float32)
+    idx, dist = knn.build(x).search(9)
+    assert_knn_equal(idx, dist, *oracle.knn_brute(x, 9), "identical")
+    assert (dist == 0).all()
+
+
+@pytest.mark.parametrize("shape", ["line", "plane", "two_clusters"])
+def test_degenerate_geometry(knn, oracle, shape):
+    rng = np.random.default_rng(11)
+    n = 20_000
+    if shape == "line":
+        t = rng.random(n, dtype=np.float32)
+        x = np.stack([t, 2 * t, np.zeros_like(t)], 1)
+    elif shape == "plane":
+        x = np.concatenate([rng.random((n, 2), dtype=np.float32), np.full((n, 1), 3.0, np.float32)], 1)
+    else:
+        a = rng.normal(0, 1e-3, (n // 2, 3)).astype(np.float32)
+        b = (rng.normal(0, 1e-3, (n // 2, 3)) + 1000.0).astype(np.float32)
+        x = np.concatenate([a, b])
+    x = np.ascontiguousarray(x, np.float32)
+    idx, dist = knn.build(x).search(8)
+    assert_knn_equal(idx, dist, *oracle.knn_kdtree(x, 8), shape)
+
+
+def test_two_dimensional_input(knn, oracle):
+    """dim == 2 => z = 0 (hostCode.cpp:114-118)."""
+    rng = np.random.default_rng(2)
+    xy = rng.random((10_000, 2), dtype=np.float32)
+    idx, dist = knn.build(xy, dim=2).search(6)
+    x3 = np.concatenate([xy, np.zeros((xy.shape[0], 1), np.float32)], 1)
+    assert_knn_equal(idx, dist, *oracle.knn_kdtree(x3, 6), "2-D")
+    # a strided 3-column array read as 2-D ignores the third column
+    junk = np.concatenate([xy, rng.random((xy.shape[0], 1), dtype=np.float32)], 1)
+    idx2, dist2 = knn.build(junk, dim=2).search(6)
+    assert (idx2 == idx).all() and (dist2 == dist).all()
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 31, 32, 33, 64, 65, 1000])
+def test_small_and_k_equals_n_minus_1(knn, oracle, n):
+    rng = np.random.default_rng(n)
+    x = rng.random((n, 3), dtype=np.float32)
+    for k in sorted({1, min(5, n - 1), n - 1}):
+        if k > 512:
+            continue
+        idx, dist = knn.build(x).search(k)
+        assert_knn_equal(idx, dist, *oracle.knn_brute(x, k), f"n={n} k={k}")
+
+
+@pytest.mark.parametrize("r0", [1e-4, 0.003, 0.02, 0.5, float("inf"), 0.0, -1.0])
+def test_start_radius_does_not_change_results(knn, oracle, r0):
+    """Rounds (hostCode.cpp:285-340) are an execution strategy: any start radius gives the exact answer."""
+    x = datasets.uniform(50_000, seed=9)
+    ref = oracle.knn_kdtree(x, 10)
+    idx, dist = knn.build(x).search(10, start_radius=r0)
+    assert_knn_equal(idx, dist, *ref, f"r0={r0}")
+    st = knn.stats()
+    if r0 == 1e-4:
+        assert st["rounds"] > 4  # doubling from a tiny radius takes several rounds
+        assert st["round_queries"][0] == 50_000 and st["round_queries"][1] <= 50_000
+    if r0 == float("inf"):
+        assert st["rounds"] == 1
+
+
+def test_clustered_lidar_like_k64(knn, oracle):
+    """cfg3 shape at 300K points: skewed density, duplicates, k = 64."""
+    x = datasets.lidar_like(300_000, seed=7)
+    idx, dist = knn.build(x).search(64)
+    assert_knn_equal(idx, dist, *oracle.knn_kdtree(x, 64), "lidar k=64")
+
+
+@pytest.mark.parametrize("leaf,policy", [(4, 0), (8, 0), (16, 0), (32, 0), (32, 1), (8, 1)])
+def test_leaf_options_are_result_invariant(knn, oracle, leaf, policy):
+    x = datasets.lidar_like(40_000, seed=3)
+    ref = oracle.knn_kdtree(x, 12)
+    knn.set_option("leaf_size", leaf)
+    knn.set_option("leaf_policy", policy)
+    idx, dist = knn.build(x).search(12)
+    assert_knn_equal(idx, dist, *ref, f"leaf={leaf} policy={policy}")
+
+
+def test_counters_and_stats(knn, oracle):
+    x = datasets.uniform(60_000, seed=1)
+    knn.set_option("counters", 1)
+    idx, dist = knn.build(x).search(10)
+    assert_knn_equal(idx, dist, *oracle.knn_kdtree(x, 10), "counters build")
+    st = knn.stats()
+    assert st["points_tested"] >= 10 * 60_000 and st["nodes_visited"] > 0 and st["heap_inserts"] >= 10 * 60_000
+    assert st["warp_point_loads"] * 32 >= st["points_tested"]
+    assert st["n_leaves"] == st["n_nodes"] + 1 and st["build_ms"] > 0 and st["search_ms"] > 0
+
+
+def test_query_sharded_union_equals_full(knn, oracle):
+    x = datasets.uniform(70_001, seed=4)
+    ref = oracle.knn_kdtree(x, 10)
+    knn.build(x)
+    for shards in (1, 2, 3, 8):
+        seen = np.zeros(x.shape[0], bool)
+        for s in range(shards):
+            qid, idx, dist = knn.search_shard(10, s, shards)
+            assert not seen[qid].any()
+            seen[qid] = True
+            assert_knn_equal(idx, dist, ref[0][qid], ref[1][qid], f"shard {s}/{shards}")
+        assert seen.all()
+
+
+def test_separate_query_set(knn, oracle):
+    rng = np.random.default_rng(8)
+    x = datasets.uniform(40_000, seed=6)
+    q = (rng.random((5_003, 3), dtype=np.float32) * 1.2 - 0.1).astype(np.float32)  # some outside the scene box
+    knn.build(x)
+    idx, dist = knn.query(q, 9)
+    assert_knn_equal(idx, dist, *oracle.knn_brute_queries(x, q, 9), "query set")
+    # data points as queries with their own index excluded == all-points search
+    sub = rng.choice(x.shape[0], 3000, replace=False).astype(np.int32)
+    idx, dist = knn.query(x[sub], 9, self_ids=sub)
+    full = oracle.knn_kdtree(x, 9)
+    assert_knn_equal(idx, dist, full[0][sub], full[1][sub], "query with self ids")
+    # per-query radius caps (boundary queries of the point-partitioned driver)
+    rad = rng.random(q.shape[0], dtype=np.float32) * 0.05
+    idx, dist = knn.query(q, 9, init_radius=rad)
+    for i in range(0, q.shape[0], 50):
+        ri, rd = oracle.knn_brute_queries(x, q[i:i + 1], 9, radius2=np.float32(rad[i]) * np.float32(rad[i]))
+        assert (idx[i] == ri[0]).all() and (dist[i] == rd[0]).all()
+
+
+def test_range_count(knn, oracle):
+    x = datasets.uniform(8_000, seed=12)
+    knn.build(x)
+    for r in (0.0, 0.01, 0.05, 0.2):
+        got = knn.range_count(r)
+        assert (np.asarray(got).astype(np.uint32) == oracle.range_count(x, r)).all(), r
+
+
+def test_gpu_brute_force_second_oracle(knn, oracle):
+    x = datasets.lidar_like(50_000, seed=2)
+    knn.build(x)
+    ids = np.random.default_rng(0).choice(x.shape[0], 777, replace=False).astype(np.int32)
+    idx, dist = knn.brute_force(ids, 20)
+    ref = oracle.knn_kdtree(x, 20)
+    assert_knn_equal(idx, dist, ref[0][ids], ref[1][ids], "gpu brute force")
+
+
+def test_estimated_radius_is_plausible(knn):
+    x = datasets.uniform(200_000, seed=42)
+    knn.build(x)
+    r = knn.estimate_start_radius(10)
+    expect = (10 / (4.0 / 3.0 * np.pi * 200_000)) ** (1 / 3)
+    assert 0.5 * expect < r < 3 * expect
+
+
+def test_device_generator_matches_numpy(knn):
+    a = knn.generate_uniform(42, 1000, 5000)
+    assert (a == datasets.uniform(5000, seed=42, first=1000)).all()
+
+
+def test_errors(knn):
+    x = datasets.uniform(100, seed=1)
+    with pytest.raises(TrueKNNError) as e:
+        knn.search(3)
+    assert e.value.code == 5  # TKNN_ESTATE: search before build
+    knn.build(x)
+    for bad_k in (0, 100, 513):
+        with pytest.raises(TrueKNNError) as e:
+            knn.search(bad_k)  # the reference never terminates for k > n-1 (hostCode.cpp:285,321-323)
+        assert e.value.code == 1
+    y = x.copy()
+    y[7, 1] = np.nan
+    with pytest.raises(TrueKNNError) as e:
+        knn.build(y)
+    assert e.value.code == 1
+    with pytest.raises(TrueKNNError):
+        knn.build(x[:1])
+    with pytest.raises(TrueKNNError):
+        knn.build(x, dim=4)
+
+
+def test_rebuild_many_times(knn, oracle):
+    """Shape of the reference's tests/t02-group-rebuilds: rebuild repeatedly, stay correct, no leak."""
+    rng = np.random.default_rng(0)
+    for it in range(30):
+        n = int(rng.integers(50, 5000))
+        x = rng.random((n, 3), dtype=np.float32)
+        idx, dist = knn.build(x).search(4)
+        if it % 10 == 0:
+            assert_knn_equal(idx, dist, *oracle.knn_brute(x, 4), f"rebuild {it}")
+
+
+def test_torch_device_tensors(knn, oracle):
+    import torch
+
+    x = datasets.uniform(20_000, seed=5)
+    xd = torch.from_numpy(x).cuda()
+    knn.set_stream(torch.cuda.current_stream().cuda_stream)
+    idx, dist = knn.build(xd).search(10)
+    assert idx.is_cuda and dist.is_cuda
+    assert_knn_equal(idx.cpu().numpy(), dist.cpu().numpy(), *oracle.knn_kdtree(x, 10), "torch tensors")
