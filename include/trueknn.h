@@ -62,6 +62,7 @@ enum {
   TKNN_OPT_SQUARED_DIST = 6,  /* 1: dist_out receives d2 instead of sqrtf(d2)                      */
   TKNN_OPT_RADIUS_QUANTILE = 7 /* start-radius estimator: per-mille quantile of the sampled k-th
                                   neighbour distance (default 990)                                */
+  ,TKNN_OPT_KEEP_SCRATCH = 8   /* 1 (default): keep the build scratch buffers for the next tknn_build    */
 };
 
 typedef struct tknn_ctx tknn_ctx;
@@ -88,7 +89,8 @@ typedef struct tknn_stats {
   float estimate_ms;  /* start-radius estimator (0 when the caller gave a radius) */
   float search_ms;    /* first launch -> last result written on device, all rounds, incl. estimate */
   float d2h_ms;       /* device->host copy of results (0 for device output)       */
-  float round_ms[TKNN_MAX_ROUNDS];
+  float round_ms[TKNN_MAX_ROUNDS];  /* round incl. compaction + the host termination check */
+  float kernel_ms[TKNN_MAX_ROUNDS]; /* the traversal kernel alone, CUDA events on the launching stream */
   uint64_t round_queries[TKNN_MAX_ROUNDS]; /* queries active in each round */
   uint32_t kernel_launches; /* kernels launched by the last search */
   uint32_t build_launches;  /* kernels launched by the last build  */

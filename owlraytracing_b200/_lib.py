@@ -18,8 +18,8 @@ TKNN_MAX_K = 512
 OK, EINVAL, ENOMEM, ECUDA, ENCCL, ESTATE = 0, 1, 2, 3, 4, 5
 ERROR_NAMES = {0: "TKNN_OK", 1: "TKNN_EINVAL", 2: "TKNN_ENOMEM", 3: "TKNN_ECUDA", 4: "TKNN_ENCCL", 5: "TKNN_ESTATE"}
 
-OPT_LEAF_SIZE, OPT_COUNTERS, OPT_LEAF_POLICY, OPT_SAMPLE_GROUPS, OPT_BLOCKS_PER_SM, OPT_SQUARED_DIST, OPT_RADIUS_QUANTILE = (
-    1, 2, 3, 4, 5, 6, 7)
+(OPT_LEAF_SIZE, OPT_COUNTERS, OPT_LEAF_POLICY, OPT_SAMPLE_GROUPS, OPT_BLOCKS_PER_SM, OPT_SQUARED_DIST, OPT_RADIUS_QUANTILE,
+ OPT_KEEP_SCRATCH) = (1, 2, 3, 4, 5, 6, 7, 8)
 
 
 class Stats(C.Structure):
@@ -44,6 +44,7 @@ class Stats(C.Structure):
         ("search_ms", C.c_float),
         ("d2h_ms", C.c_float),
         ("round_ms", C.c_float * TKNN_MAX_ROUNDS),
+        ("kernel_ms", C.c_float * TKNN_MAX_ROUNDS),
         ("round_queries", C.c_uint64 * TKNN_MAX_ROUNDS),
         ("kernel_launches", C.c_uint32),
         ("build_launches", C.c_uint32),
@@ -61,7 +62,7 @@ class Stats(C.Structure):
         d = {}
         for name, _ in self._fields_:
             v = getattr(self, name)
-            if name in ("round_ms", "round_queries"):
+            if name in ("round_ms", "kernel_ms", "round_queries"):
                 v = list(v)[: max(0, int(self.rounds))]
             d[name] = v
         return d

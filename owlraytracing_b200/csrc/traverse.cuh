@@ -81,6 +81,21 @@ __device__ __forceinline__ void heap_sift_root(uint64_t* H, int size, uint64_t k
   H[i * 32] = key;
 }
 
+// ---- bounded ASCENDING list of u64 keys in shared memory (slot s of lane l at L[s * 32 + l]) ----
+// Candidates arrive roughly nearest-first, so a new key usually lands near the tail: the backward
+// shift is short, and the list needs no heap-sort at emit time.  Precondition: cnt < k or key < L[k-1].
+__device__ __forceinline__ void list_insert(uint64_t* L, int& cnt, int k, uint64_t key) {
+  int i = cnt < k ? cnt : k - 1;
+  while (i > 0) {
+    const uint64_t prev = L[(i - 1) * 32];
+    if (prev <= key) break;
+    L[i * 32] = prev;
+    --i;
+  }
+  L[i * 32] = key;
+  if (cnt < k) ++cnt;
+}
+
 __host__ __device__ inline size_t smem_per_warp(int k) {
   return (size_t)k * 32 * sizeof(uint64_t) + 32 * sizeof(float4) + STACK_DEPTH * sizeof(int);
 }
@@ -151,12 +166,20 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
             cnt += (d <= bound && __float_as_int(p.w) != self) ? 1 : 0;
           }
         } else {
+          // filter: 8 points per step with compile-time bit positions; slots >= lcount hold stale
+          // points whose bits are masked off afterwards
           uint32_t mask = 0;
-          for (int j = 0; j < lcount; ++j) {
-            const float4 p = stage[j];
-            const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
-            mask |= (d <= bound ? 1u : 0u) << j;
+          for (int j0 = 0; j0 < lcount; j0 += 8) {
+            uint32_t m8 = 0;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const float4 p = stage[j0 + jj];
+              const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+              if (d <= bound) m8 |= (1u << jj);
+            }
+            mask |= m8 << j0;
           }
+          if (lcount < 32) mask &= (1u << lcount) - 1u;
           while (__any_sync(FULL_MASK, mask != 0u)) {
             if (mask) {
               const int j = __ffs(mask) - 1;
@@ -166,13 +189,9 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
               const int pid = __float_as_int(p.w);
               if (pid != self && d <= bound) {
                 const uint64_t key = make_key(d, pid);
-                if (cnt < k) {
-                  heap_push(H, cnt, key);
-                  if (cnt == k) bound = key_d2(H[0]);
-                  if (COUNT) c_ins += 1;
-                } else if (key < H[0]) {
-                  heap_sift_root(H, k, key);
-                  bound = key_d2(H[0]);
+                if (cnt < k || key < H[(k - 1) * 32]) {
+                  list_insert(H, cnt, k, key);
+                  if (cnt == k) bound = key_d2(H[(k - 1) * 32]);
                   if (COUNT) c_ins += 1;
                 }
               }
@@ -221,11 +240,10 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
         float* dd = P.dist_out + row * (uint64_t)k;
         if (P.row_mode && P.qid_out) P.qid_out[row] = row_id;
         for (int i = k - 1; i >= cnt; --i) { io[i] = -1; dd[i] = FLT_MAX; }
-        for (int i = cnt - 1; i >= 0; --i) {  // heap-sort extraction, largest first
-          const uint64_t top = H[0];
-          io[i] = key_idx(top);
-          dd[i] = P.squared ? key_d2(top) : __fsqrt_rn(key_d2(top));
-          if (i > 0) heap_sift_root(H, i, H[i * 32]);
+        for (int i = 0; i < cnt; ++i) {
+          const uint64_t e = H[i * 32];
+          io[i] = key_idx(e);
+          dd[i] = P.squared ? key_d2(e) : __fsqrt_rn(key_d2(e));
         }
       }
     }

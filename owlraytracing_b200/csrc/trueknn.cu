@@ -48,6 +48,10 @@ struct tknn_ctx {
   float scene_box[6] = {0, 0, 0, 0, 0, 0};
   // search scratch (grown on demand, kept across searches)
   DevBuf queue_a, queue_b, unresolved, offsets, block_sums, scalars, stage_idx, stage_dist, sample;
+  // build scratch, kept across builds (grow-only) unless keep_scratch == 0
+  DevBuf b_in, b_keys_a, b_keys_b, b_vals_a, b_vals_b, b_sort_tmp, b_delta, b_ballots, b_leaf_key, b_child_info,
+      b_parent_leaf, b_parent_node, b_arrive;
+  int keep_scratch = 1;
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> round_ev;
   tknn_stats stats;
@@ -225,18 +229,19 @@ int run_rounds(tknn_ctx* c, const Job& job, int* launches_io) {
     P.counters = c->counters ? reinterpret_cast<unsigned long long*>(sc + SC_COUNTERS) : nullptr;
 
     if (job.record_stats && round < TKNN_MAX_ROUNDS) {
-      if ((int)c->round_ev.size() < 2 * (round + 1)) {
-        cudaEvent_t a, b;
+      while ((int)c->round_ev.size() < 4 * (round + 1)) {
+        cudaEvent_t a;
         TK_CUDA(c, cudaEventCreate(&a));
-        TK_CUDA(c, cudaEventCreate(&b));
         c->round_ev.push_back(a);
-        c->round_ev.push_back(b);
       }
-      TK_CUDA(c, cudaEventRecord(c->round_ev[2 * round], c->stream));
+      TK_CUDA(c, cudaEventRecord(c->round_ev[4 * round], c->stream));
       c->stats.round_queries[round] = active;
     }
     TK_CUDA(c, cudaMemsetAsync(sc + SC_GROUP_COUNTER, 0, sizeof(uint32_t), c->stream));
+    const bool timed = job.record_stats && round < TKNN_MAX_ROUNDS;
+    if (timed) TK_CUDA(c, cudaEventRecord(c->round_ev[4 * round + 2], c->stream));
     TK_TRY(launch_traverse<trav::MODE_KNN>(c, P));
+    if (timed) TK_CUDA(c, cudaEventRecord(c->round_ev[4 * round + 3], c->stream));
     ++launches;
 
     uint32_t next_active = 0;
@@ -254,7 +259,7 @@ int run_rounds(tknn_ctx* c, const Job& job, int* launches_io) {
         queue = qout.as<uint32_t>();
       }
     }
-    if (job.record_stats && round < TKNN_MAX_ROUNDS) TK_CUDA(c, cudaEventRecord(c->round_ev[2 * round + 1], c->stream));
+    if (timed) TK_CUDA(c, cudaEventRecord(c->round_ev[4 * round + 1], c->stream));
     ++round;
     active = next_active;
     if (!last) radius *= 2.0f;
@@ -351,8 +356,10 @@ int collect_counters(tknn_ctx* c) {
 int finish_round_stats(tknn_ctx* c) {
   for (int r = 0; r < c->stats.rounds && r < TKNN_MAX_ROUNDS; ++r) {
     float ms = 0.f;
-    TK_CUDA(c, cudaEventElapsedTime(&ms, c->round_ev[2 * r], c->round_ev[2 * r + 1]));
+    TK_CUDA(c, cudaEventElapsedTime(&ms, c->round_ev[4 * r], c->round_ev[4 * r + 1]));
     c->stats.round_ms[r] = ms;
+    TK_CUDA(c, cudaEventElapsedTime(&ms, c->round_ev[4 * r + 2], c->round_ev[4 * r + 3]));
+    c->stats.kernel_ms[r] = ms;
   }
   return TKNN_OK;
 }
@@ -362,6 +369,7 @@ void reset_search_stats(tknn_ctx* c) {
   s.n_queries = 0; s.k = 0; s.rounds = 0; s.start_radius = s.final_radius = 0.f;
   s.estimate_ms = s.search_ms = s.d2h_ms = 0.f;
   std::memset(s.round_ms, 0, sizeof(s.round_ms));
+  std::memset(s.kernel_ms, 0, sizeof(s.kernel_ms));
   std::memset(s.round_queries, 0, sizeof(s.round_queries));
   s.kernel_launches = 0;
   s.nodes_visited = s.points_tested = s.heap_inserts = 0;
@@ -492,7 +500,9 @@ int tknn_destroy(tknn_ctx* c) {
   ScopedDevice sd(c->device);
   cudaStreamSynchronize(c->stream);
   for (DevBuf* b : {&c->pts, &c->nodes, &c->leaf_start, &c->queue_a, &c->queue_b, &c->unresolved, &c->offsets,
-                    &c->block_sums, &c->scalars, &c->stage_idx, &c->stage_dist, &c->sample})
+                    &c->block_sums, &c->scalars, &c->stage_idx, &c->stage_dist, &c->sample, &c->b_in, &c->b_keys_a,
+                    &c->b_keys_b, &c->b_vals_a, &c->b_vals_b, &c->b_sort_tmp, &c->b_delta, &c->b_ballots, &c->b_leaf_key,
+                    &c->b_child_info, &c->b_parent_leaf, &c->b_parent_node, &c->b_arrive})
     release(*b);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->round_ev) cudaEventDestroy(ev);
@@ -528,6 +538,7 @@ int tknn_set_option(tknn_ctx* c, int key, int64_t value) {
       c->blocks_per_sm = (int)value;
       return TKNN_OK;
     case TKNN_OPT_SQUARED_DIST: c->squared = value ? 1 : 0; return TKNN_OK;
+    case TKNN_OPT_KEEP_SCRATCH: c->keep_scratch = value ? 1 : 0; return TKNN_OK;
     case TKNN_OPT_RADIUS_QUANTILE:
       if (value < 0 || value > 1000) return fail(c, TKNN_EINVAL, "radius quantile outside [0, 1000] per mille");
       c->radius_quantile = (int)value;
@@ -553,13 +564,32 @@ int tknn_build(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int stride_fl
   int launches = 0;
 
   // ---- stage the input ----
-  DevBuf in_stage, keys_a, keys_b, vals_a, vals_b, sort_tmp, delta, ballots, leaf_key, child_info, parent_leaf, parent_node,
-      arrive;
+  DevBuf &in_stage = c->b_in, &keys_a = c->b_keys_a, &keys_b = c->b_keys_b, &vals_a = c->b_vals_a, &vals_b = c->b_vals_b,
+         &sort_tmp = c->b_sort_tmp, &delta = c->b_delta, &ballots = c->b_ballots, &leaf_key = c->b_leaf_key,
+         &child_info = c->b_child_info, &parent_leaf = c->b_parent_leaf, &parent_node = c->b_parent_node, &arrive = c->b_arrive;
   auto cleanup = [&]() {
+    if (c->keep_scratch) return;
     for (DevBuf* b : {&in_stage, &keys_a, &keys_b, &vals_a, &vals_b, &sort_tmp, &delta, &ballots, &leaf_key, &child_info,
                       &parent_leaf, &parent_node, &arrive})
       release(*b);
   };
+  // size-only allocations happen before the timed region (cudaMalloc is a synchronous host call)
+  {
+    const uint64_t nw0 = (n + 31) / 32;
+    int rc0 = TKNN_OK;
+    if (!is_device_ptr(xyz)) rc0 = ensure(c, in_stage, (size_t)n * stride_floats * sizeof(float));
+    if (rc0 == TKNN_OK) rc0 = ensure(c, keys_a, n * sizeof(uint64_t));
+    if (rc0 == TKNN_OK) rc0 = ensure(c, keys_b, n * sizeof(uint64_t));
+    if (rc0 == TKNN_OK) rc0 = ensure(c, vals_a, n * sizeof(uint32_t));
+    if (rc0 == TKNN_OK) rc0 = ensure(c, vals_b, n * sizeof(uint32_t));
+    if (rc0 == TKNN_OK) rc0 = ensure(c, sort_tmp, rsort::temp_words(n) * sizeof(uint32_t));
+    if (rc0 == TKNN_OK) rc0 = ensure(c, delta, n);
+    if (rc0 == TKNN_OK) rc0 = ensure(c, ballots, nw0 * sizeof(uint32_t));
+    if (rc0 == TKNN_OK) rc0 = ensure(c, c->offsets, (nw0 + 1) * sizeof(uint32_t));
+    if (rc0 == TKNN_OK) rc0 = ensure(c, c->block_sums, sizeof(uint32_t) * (size_t)(nw0 / lbvh::SCAN_CHUNK + 2));
+    if (rc0 == TKNN_OK) rc0 = ensure(c, c->pts, n * sizeof(float4));
+    if (rc0 != TKNN_OK) { cleanup(); return rc0; }
+  }
 #define TK_B(expr) do { int rc_ = (expr); if (rc_ != TKNN_OK) { cleanup(); return rc_; } } while (0)
 #define TK_BC(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cudaGetLastError(); cleanup(); \
     return fail(c, e_ == cudaErrorMemoryAllocation ? TKNN_ENOMEM : TKNN_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); } } while (0)

@@ -1,0 +1,201 @@
+"""CPU suite (no GPU): the oracle against its own ground truth, the committed golden vectors and
+the reference-semantics pin; host logic; the C ABI surface."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from owlraytracing_b200 import _lib, datasets, read_points
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+# ---------------------------------------------------------------- oracle vs ground truth
+@pytest.mark.parametrize("n,k", [(2, 1), (50, 49), (1000, 1), (1000, 10), (5000, 64)])
+def test_kdtree_equals_brute_uniform(oracle, n, k):
+    x = datasets.uniform(n, seed=n)
+    ib, db = oracle.knn_brute(x, k)
+    ik, dk = oracle.knn_kdtree(x, k)
+    assert (ib == ik).all() and (db == dk).all()
+
+
+def test_kdtree_equals_brute_adversarial(oracle):
+    rng = np.random.default_rng(0)
+    base = rng.random((800, 3), dtype=np.float32)
+    clouds = {
+        "duplicates": np.concatenate([base, base[:400], np.tile(base[:1], (100, 1))]),
+        "line": np.stack([np.linspace(0, 1, 2000, dtype=np.float32)] * 3, 1),
+        "plane": np.concatenate([rng.random((2000, 2), dtype=np.float32), np.zeros((2000, 1), np.float32)], 1),
+        "lattice": datasets.lattice(9),
+        "lidar": datasets.lidar_like(6000, seed=7),
+        "identical": np.full((300, 3), 1.5, np.float32),
+    }
+    for name, x in clouds.items():
+        x = np.ascontiguousarray(x, np.float32)
+        for k in (1, 6, 27):
+            ib, db = oracle.knn_brute(x, k)
+            ik, dk = oracle.knn_kdtree(x, k)
+            assert (ib == ik).all() and (db == dk).all(), (name, k)
+
+
+def test_lattice_known_answers(oracle):
+    """Hand-computable: interior lattice point has 6 neighbours at 1, 12 at sqrt 2, 8 at sqrt 3."""
+    m = 7
+    x = datasets.lattice(m)
+    idx, dist = oracle.knn_brute(x, 26)
+    c = 3 * m * m + 3 * m + 3
+    assert (dist[c][:6] == 1.0).all()
+    assert np.allclose(dist[c][6:18], np.sqrt(np.float32(2)), rtol=0, atol=0)
+    assert (dist[c][18:26] == np.sqrt(np.float32(3))).all()
+    # lowest-index tie-break inside each shell
+    for a, b in ((0, 6), (6, 18), (18, 26)):
+        assert (np.diff(idx[c][a:b]) > 0).all()
+    expected6 = sorted(c + d for d in (-m * m, -m, -1, 1, m, m * m))
+    assert idx[c][:6].tolist() == expected6
+    # corner point 0: its three unit neighbours are 1, m, m*m
+    assert idx[0][:3].tolist() == [1, m, m * m]
+
+
+def test_distance_formula_is_the_fma_chain(oracle):
+    rng = np.random.default_rng(1)
+    a = rng.random((200, 3)).astype(np.float32)
+    b = rng.random((200, 3)).astype(np.float32)
+    for p, q in zip(a, b):
+        d = (p - q).astype(np.float32)
+        # fmaf(dz,dz,fmaf(dy,dy,dx*dx)) evaluated exactly in float64 then rounded once per fma
+        t0 = np.float32(d[0] * d[0])
+        t1 = np.float32(np.float64(d[1]) * np.float64(d[1]) + np.float64(t0))
+        t2 = np.float32(np.float64(d[2]) * np.float64(d[2]) + np.float64(t1))
+        assert oracle.dist2(p, q) == t2
+
+
+def test_self_excluded_by_index_not_by_position(oracle):
+    x = np.array([[0, 0, 0], [0, 0, 0], [1, 0, 0]], np.float32)
+    idx, dist = oracle.knn_brute(x, 2)
+    assert idx[0].tolist() == [1, 2] and dist[0].tolist() == [0.0, 1.0]
+    assert idx[1].tolist() == [0, 2]
+
+
+# ---------------------------------------------------------------- reference semantics pin
+def test_reference_rounds_equal_exact_when_radius_covers_cloud(oracle):
+    """The reference's own rules (deviceCode.cu:62-152, hostCode.cpp:285-340) give the exact answer
+    when the first radius already covers every point: the one place its semantics and the exact
+    oracle coincide."""
+    x = datasets.uniform(2500, seed=5)
+    ib, db = oracle.knn_brute(x, 7)
+    ir, dr, rounds, _, rc = oracle.reference_trueknn(x, 7, 2.0)
+    assert rc == 0 and rounds == 1
+    assert (ir == ib).all() and (dr == db).all()
+
+
+def test_reference_rounds_are_inexact_from_a_small_radius(oracle):
+    """F2: candidates come from an L-inf cube and a query stops once k were inserted."""
+    x = datasets.uniform(4000, seed=6)
+    ib, _ = oracle.knn_brute(x, 10)
+    ir, dr, rounds, fr, rc = oracle.reference_trueknn(x, 10, 0.01)
+    assert rc == 0 and rounds > 1 and fr == pytest.approx(0.01 * 2 ** (rounds - 1))
+    wrong = np.mean([set(a) != set(b) for a, b in zip(ir, ib)])
+    assert 0.01 < wrong < 0.9
+    assert (np.diff(dr, axis=1) >= 0).all()  # still sorted (deviceCode.cu:121-134)
+
+
+def test_golden_vectors(oracle):
+    """Committed fixtures (tests/golden/make_golden.py): the oracle must keep producing them."""
+    g = np.load(os.path.join(GOLDEN, "knn_golden.npz"))
+    for name in ("uniform", "lidar", "lattice", "dups"):
+        x, k = g[f"{name}_x"], int(g[f"{name}_k"])
+        idx, dist = oracle.knn_kdtree(x, k)
+        assert (idx == g[f"{name}_idx"]).all(), name
+        assert (dist == g[f"{name}_dist"]).all(), name
+    assert (datasets.uniform(64, seed=42) == g["hash_uniform_seed42_first64"]).all()
+
+
+# ---------------------------------------------------------------- host logic
+def test_point_file_grammar_matches_reference_restatement(oracle, tmp_path):
+    text = b"1,2,3\n4 5 6\n 7.5, 8e-1 ,9\n10,11,12,13\n14,15,16\n"
+    p = tmp_path / "pts.csv"
+    p.write_bytes(text)
+    for n, dim in ((1, 3), (3, 3), (2, 2)):
+        try:
+            want = oracle.parse_points(text, n, dim)
+        except ValueError:
+            with pytest.raises(ValueError):
+                read_points(str(p), n, dim)
+            continue
+        got = read_points(str(p), n, dim)
+        assert got.shape == want.shape and (got == want).all(), (n, dim)
+    # a row with more than `dim` columns mis-strides exactly like hostCode.cpp:95-103
+    got = read_points(str(p), 5, 2)
+    assert got[0].tolist() == [1, 2, 0] and got[1].tolist() == [3, 4, 0]
+    # binary fast path
+    x = datasets.uniform(100, seed=1)
+    b = tmp_path / "pts.f32"
+    x.tofile(str(b))
+    assert (read_points(str(b), 40, 3) == x[:40]).all()
+
+
+def test_uniform_generator_is_index_addressable():
+    a = datasets.uniform(1000, seed=42)
+    b = datasets.uniform(300, seed=42, first=500)
+    assert (a[500:800] == b).all()
+    assert a.min() >= 0 and a.max() < 1 and a.dtype == np.float32
+    assert abs(a.mean() - 0.5) < 0.02
+
+
+def test_lidar_generator_shape():
+    x = datasets.lidar_like(50_000, seed=7)
+    assert x.shape == (50_000, 3) and np.isfinite(x).all()
+    _, counts = np.unique(x, axis=0, return_counts=True)
+    assert (counts > 1).sum() >= 40  # the 0.1 % exact duplicates
+
+
+# ---------------------------------------------------------------- the C ABI surface (no compute without a GPU)
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "trueknn.h")).read()
+    declared = sorted(set(re.findall(r"TKNN_API\s+[\w\s\*]+?\b(tknn_\w+)\s*\(", header)))
+    assert declared == sorted(_lib.EXPORTS)
+    L = _lib.load()
+    for name in declared:
+        assert hasattr(L, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (\w+)", out))
+    assert set(declared) <= exported
+    assert not [s for s in exported if not s.startswith("tknn_") and not s.startswith("_")]  # nothing else leaks
+    assert L.tknn_version() == 100
+
+
+def test_stats_struct_layout_matches_header():
+    src = "#include <stdio.h>\n#include \"trueknn.h\"\nint main(){printf(\"%zu %zu %zu\", sizeof(tknn_stats), " \
+          "__builtin_offsetof(tknn_stats, round_ms), __builtin_offsetof(tknn_stats, h2d_bytes));return 0;}"
+    exe = "/tmp/tknn_layout"
+    subprocess.run(["/usr/bin/gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src, text=True,
+                   check=True)
+    size, off_round, off_h2d = (int(v) for v in subprocess.run([exe], capture_output=True, text=True).stdout.split())
+    assert size == ctypes.sizeof(_lib.Stats)
+    assert off_round == _lib.Stats.round_ms.offset and off_h2d == _lib.Stats.h2d_bytes.offset
+
+
+def test_no_cpu_fallback_without_a_device():
+    """Without a usable CUDA device tknn_create fails; nothing silently computes on the host."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from owlraytracing_b200 import TrueKNN, TrueKNNError
+
+    with pytest.raises(TrueKNNError) as e:
+        TrueKNN(0)
+    assert e.value.code == _lib.ECUDA
+
+
+def test_product_code_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "owlraytracing_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "liboracle" not in text and "from oracle" not in text and "import oracle" not in text, f
