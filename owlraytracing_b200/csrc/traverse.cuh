@@ -85,19 +85,19 @@ __device__ __forceinline__ void heap_sift_root(uint64_t* H, int size, uint64_t k
 // Candidates arrive roughly nearest-first, so a new key usually lands near the tail: the backward
 // shift is short, and the list needs no heap-sort at emit time.  Precondition: cnt < k or key < L[k-1].
 __device__ __forceinline__ void list_insert(uint64_t* L, int& cnt, int k, uint64_t key) {
-  int i = cnt < k ? cnt : k - 1;
-  while (i > 0) {
-    const uint64_t prev = L[(i - 1) * 32];
+  uint64_t* p = L + (cnt < k ? cnt : k - 1) * 32;
+  while (p != L) {
+    const uint64_t prev = *(p - 32);
     if (prev <= key) break;
-    L[i * 32] = prev;
-    --i;
+    *p = prev;
+    p -= 32;
   }
-  L[i * 32] = key;
+  *p = key;
   if (cnt < k) ++cnt;
 }
 
 __host__ __device__ inline size_t smem_per_warp(int k) {
-  return (size_t)k * 32 * sizeof(uint64_t) + 32 * sizeof(float4) + STACK_DEPTH * sizeof(int);
+  return (size_t)k * 32 * sizeof(uint64_t) + MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int);
 }
 
 template <int MODE, bool COUNT>
@@ -107,8 +107,8 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
   const int k = P.k;
   unsigned char* wbase = smem + (size_t)warp * smem_per_warp(MODE == MODE_KNN ? k : 0);
   float4* stage = reinterpret_cast<float4*>(wbase);
-  int* stack = reinterpret_cast<int*>(wbase + 32 * sizeof(float4));
-  uint64_t* H = reinterpret_cast<uint64_t*>(wbase + 32 * sizeof(float4) + STACK_DEPTH * sizeof(int)) + lane;
+  int* stack = reinterpret_cast<int*>(wbase + MAX_LEAF * sizeof(float4));
+  uint64_t* H = reinterpret_cast<uint64_t*>(wbase + MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int)) + lane;
 
   unsigned long long c_nodes = 0, c_tests = 0, c_ins = 0, c_wnodes = 0, c_wleaves = 0, c_wpts = 0;
 
@@ -142,70 +142,78 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
       if (COUNT) { c_nodes += valid ? 1 : 0; c_wnodes += 1; }
       const int ref0 = __float_as_int(lo0.w), cnt0 = __float_as_int(hi0.w);
       const int ref1 = __float_as_int(lo1.w), cnt1 = __float_as_int(hi1.w);
-      // near-first among the two children, by majority of lanes
-      const unsigned closer1 = __ballot_sync(FULL_MASK, d1 < d0);
-      const unsigned closer0 = __ballot_sync(FULL_MASK, d0 < d1);
-      const bool swap = __popc(closer1) > __popc(closer0);
 
       // ---- leaf children first (they tighten the bounds before anything is pushed) ----
+      if ((cnt0 | cnt1) != 0) {
+        // near-first among two leaves, by majority of lanes
+        bool swap = false;
+        if (cnt0 > 0 && cnt1 > 0)
+          swap = __popc(__ballot_sync(FULL_MASK, d1 < d0)) > __popc(__ballot_sync(FULL_MASK, d0 < d1));
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        const bool second = (c == 1) != swap;  // false: child 0, true: child 1
-        const int lcount = second ? cnt1 : cnt0;
-        if (lcount <= 0) continue;
-        const float dc = second ? d1 : d0;
-        if (!__any_sync(FULL_MASK, dc <= bound)) continue;
-        const int start = second ? ref1 : ref0;
-        if (lane < lcount) stage[lane] = __ldg(&P.pts[(uint64_t)(uint32_t)start + lane]);
-        __syncwarp();
-        if (COUNT) { c_tests += valid ? lcount : 0; c_wleaves += 1; c_wpts += lcount; }
-        if (MODE == MODE_RANGE_COUNT) {
-          for (int j = 0; j < lcount; ++j) {
-            const float4 p = stage[j];
-            const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
-            cnt += (d <= bound && __float_as_int(p.w) != self) ? 1 : 0;
-          }
-        } else {
-          // filter: 8 points per step with compile-time bit positions; slots >= lcount hold stale
-          // points whose bits are masked off afterwards
-          uint32_t mask = 0;
-          for (int j0 = 0; j0 < lcount; j0 += 8) {
-            uint32_t m8 = 0;
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              const float4 p = stage[j0 + jj];
-              const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
-              if (d <= bound) m8 |= (1u << jj);
-            }
-            mask |= m8 << j0;
-          }
-          if (lcount < 32) mask &= (1u << lcount) - 1u;
-          while (__any_sync(FULL_MASK, mask != 0u)) {
-            if (mask) {
-              const int j = __ffs(mask) - 1;
-              mask &= mask - 1u;
+        for (int c = 0; c < 2; ++c) {
+          const bool second = (c == 1) != swap;  // false: child 0, true: child 1
+          const int lcount = second ? cnt1 : cnt0;
+          if (lcount <= 0) continue;
+          const float dc = second ? d1 : d0;
+          if (!__any_sync(FULL_MASK, dc <= bound)) continue;
+          const int start = second ? ref1 : ref0;
+          if (lane < lcount) stage[lane] = __ldg(&P.pts[(uint64_t)(uint32_t)start + lane]);
+          __syncwarp();
+          if (COUNT) { c_tests += valid ? lcount : 0; c_wleaves += 1; c_wpts += lcount; }
+          if (MODE == MODE_RANGE_COUNT) {
+            for (int j = 0; j < lcount; ++j) {
               const float4 p = stage[j];
               const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
-              const int pid = __float_as_int(p.w);
-              if (pid != self && d <= bound) {
-                const uint64_t key = make_key(d, pid);
-                if (cnt < k || key < H[(k - 1) * 32]) {
-                  list_insert(H, cnt, k, key);
-                  if (cnt == k) bound = key_d2(H[(k - 1) * 32]);
-                  if (COUNT) c_ins += 1;
+              cnt += (d <= bound && __float_as_int(p.w) != self) ? 1 : 0;
+            }
+          } else {
+            // filter: full chunks of 8 with compile-time bit positions, then the remainder one by one
+            uint32_t mask = 0;
+            int j0 = 0;
+            for (; j0 + 8 <= lcount; j0 += 8) {
+              uint32_t m8 = 0;
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                const float4 p = stage[j0 + jj];
+                const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+                if (d <= bound) m8 |= (1u << jj);
+              }
+              mask |= m8 << j0;
+            }
+            for (; j0 < lcount; ++j0) {
+              const float4 p = stage[j0];
+              const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+              if (d <= bound) mask |= (1u << j0);
+            }
+            // insert: only lanes with survivors do work; the bound tightens as they go
+            while (__any_sync(FULL_MASK, mask != 0u)) {
+              if (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                const float4 p = stage[j];
+                const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+                const int pid = __float_as_int(p.w);
+                if (pid != self && d <= bound) {
+                  const uint64_t key = make_key(d, pid);
+                  if (cnt < k || key < H[(k - 1) * 32]) {
+                    list_insert(H, cnt, k, key);
+                    if (cnt == k) bound = key_d2(H[(k - 1) * 32]);
+                    if (COUNT) c_ins += 1;
+                  }
                 }
               }
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
 
-      // ---- internal children, re-voted against the tightened bounds ----
-      const bool w0 = (cnt0 == 0) && (ref0 >= 0) && __any_sync(FULL_MASK, d0 <= bound);
-      const bool w1 = (cnt1 == 0) && (ref1 >= 0) && __any_sync(FULL_MASK, d1 <= bound);
+      // ---- internal children, voted against the (tightened) bounds ----
+      const bool w0 = (cnt0 == 0) && __any_sync(FULL_MASK, d0 <= bound);
+      const bool w1 = (cnt1 == 0) && __any_sync(FULL_MASK, d1 <= bound);
       if (w0 && w1) {
-        const int nearc = swap ? ref1 : ref0, farc = swap ? ref0 : ref1;
+        const bool far0 = __popc(__ballot_sync(FULL_MASK, d1 < d0)) > __popc(__ballot_sync(FULL_MASK, d0 < d1));
+        const int nearc = far0 ? ref1 : ref0, farc = far0 ? ref0 : ref1;
         if (sp < STACK_DEPTH) {
           if (lane == 0) stack[sp] = farc;
           ++sp;
@@ -223,7 +231,6 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
         __syncwarp();
         node = stack[sp];
       }
-      __syncwarp();
     }
 
     // ---- emit ----
