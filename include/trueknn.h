@@ -63,6 +63,8 @@ enum {
   TKNN_OPT_RADIUS_QUANTILE = 7 /* start-radius estimator: per-mille quantile of the sampled k-th
                                   neighbour distance (default 990)                                */
   ,TKNN_OPT_KEEP_SCRATCH = 8   /* 1 (default): keep the build scratch buffers for the next tknn_build    */
+  ,TKNN_OPT_SPARSE_DIVISOR = 9 /* rounds >= 2 with fewer than n/divisor active queries run the
+                                  thread-per-query kernel (default 8; 0 = never)                  */
 };
 
 typedef struct tknn_ctx tknn_ctx;

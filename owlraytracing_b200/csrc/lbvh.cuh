@@ -132,28 +132,37 @@ __global__ void __launch_bounds__(THREADS) delta_kernel(const uint64_t* __restri
 __global__ void __launch_bounds__(THREADS) leaf_flag_kernel(const uint8_t* __restrict__ delta, uint64_t n, int leaf_max,
                                                             int policy, uint64_t force_split,
                                                             uint32_t* __restrict__ ballots) {
-  const uint64_t b = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
+  // the block's boundaries plus a halo of MAX_LEAF on both sides, staged once in shared memory
+  __shared__ uint8_t s_delta[THREADS + 2 * MAX_LEAF];
+  const int64_t block0 = (int64_t)blockIdx.x * THREADS;
+  const int64_t in = (int64_t)n;
+  for (int i = threadIdx.x; i < THREADS + 2 * MAX_LEAF; i += THREADS) {
+    const int64_t g = block0 - MAX_LEAF + i;
+    s_delta[i] = (g >= 0 && g < in) ? delta[g] : 0;
+  }
+  __syncthreads();
+  const int64_t ib = block0 + threadIdx.x;
+  const uint8_t* w = s_delta + MAX_LEAF + threadIdx.x;  // w[o] = delta[ib + o]
   bool cut = false;
-  if (b < n) {
-    if (b == 0 || (force_split && b == force_split)) cut = true;
-    else if (policy == 1) cut = (b % (uint64_t)leaf_max) == 0;
+  if (ib < in) {
+    if (ib == 0 || (force_split && (uint64_t)ib == force_split)) cut = true;
+    else if (policy == 1) cut = (ib % leaf_max) == 0;
     else {
-      const int s = delta[b];
-      const int64_t ib = (int64_t)b, in = (int64_t)n;
+      const int s = w[0];
       int64_t l = -1, r = -1;
-      int64_t jlo = ib - leaf_max + 1;
-      for (int64_t j = ib - 1; j >= 1 && j >= jlo; --j)
-        if (delta[j] < s) { l = j; break; }
+      const int64_t jlo = ib - leaf_max + 1;
+      for (int o = -1; ib + o >= 1 && ib + o >= jlo; --o)
+        if (w[o] < s) { l = ib + o; break; }
       if (l < 0 && jlo <= 0) l = 0;
-      int64_t jhi = ib + leaf_max - 1;
-      for (int64_t j = ib + 1; j <= in - 1 && j <= jhi; ++j)
-        if (delta[j] < s) { r = j; break; }
+      const int64_t jhi = ib + leaf_max - 1;
+      for (int o = 1; ib + o <= in - 1 && ib + o <= jhi; ++o)
+        if (w[o] < s) { r = ib + o; break; }
       if (r < 0 && jhi >= in) r = in;
       cut = (l < 0) || (r < 0) || (r - l > leaf_max);
     }
   }
-  const uint32_t w = __ballot_sync(FULL_MASK, cut);
-  if ((threadIdx.x & 31) == 0 && b < n) ballots[b >> 5] = w;
+  const uint32_t word = __ballot_sync(FULL_MASK, cut);
+  if ((threadIdx.x & 31) == 0 && ib < in) ballots[ib >> 5] = word;
 }
 
 // ------------------------------------------------------------------------------------------------

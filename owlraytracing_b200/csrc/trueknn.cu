@@ -52,6 +52,7 @@ struct tknn_ctx {
   DevBuf b_in, b_keys_a, b_keys_b, b_vals_a, b_vals_b, b_sort_tmp, b_delta, b_ballots, b_leaf_key, b_child_info,
       b_parent_leaf, b_parent_node, b_arrive;
   int keep_scratch = 1;
+  int sparse_divisor = 8;
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> round_ev;
   tknn_stats stats;
@@ -154,22 +155,26 @@ struct Job {
   float* dist_out = nullptr;
   int32_t* qid_out = nullptr;
   bool record_stats = true;
+  bool force_sparse = false;  // thread-per-query kernel from round 1 (the start-radius sample)
 };
 
 template <int MODE>
 int launch_traverse(tknn_ctx* c, const trav::Params& P) {
   const int k = MODE == trav::MODE_KNN ? P.k : 0;
   const size_t per_warp = trav::smem_per_warp(k);
-  const size_t smem_cap = 200 * 1024;
-  int warps = (int)std::min<size_t>(8, smem_cap / per_warp);
+  // block shape: the warps-per-block that keeps the most warps resident per SM (227 KB shared, 64 warps)
+  const size_t sm_smem = 227 * 1024;
+  int warps = 0, bps = 1, best = 0;
+  for (int w = 8; w >= 1; --w) {
+    const size_t need_b = per_warp * w + 1024;  // + per-block reservation
+    if (need_b > sm_smem) continue;
+    int b = (int)std::min<size_t>(sm_smem / need_b, (size_t)(64 / w));
+    b = std::min(b, 32);
+    if (b * w > best) { best = b * w; warps = w; bps = b; }
+  }
   if (warps < 1) return fail(c, TKNN_EINVAL, "k = %d needs %zu B of shared memory per warp", k, per_warp);
   const size_t smem = per_warp * warps;
-  int bps = c->blocks_per_sm;
-  if (bps <= 0) {
-    bps = (int)std::min<size_t>(16, (220 * 1024) / (smem + 1024));
-    const int by_threads = 2048 / (warps * 32);
-    bps = std::max(1, std::min(bps, by_threads));
-  }
+  if (c->blocks_per_sm > 0) bps = c->blocks_per_sm;
   uint64_t grid = (uint64_t)c->sm_count * bps;
   const uint64_t need = ((uint64_t)P.n_groups + warps - 1) / warps;
   if (grid > need) grid = std::max<uint64_t>(1, need);
@@ -181,6 +186,24 @@ int launch_traverse(tknn_ctx* c, const trav::Params& P) {
     auto kern = trav::traverse_kernel<MODE, false>;
     TK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, warps * 32, smem, c->stream>>>(P);
+  }
+  TK_CUDA(c, cudaGetLastError());
+  return TKNN_OK;
+}
+
+// thread-per-query variant for rounds whose active set is a small, spatially incoherent remainder
+int launch_traverse_sparse(tknn_ctx* c, const trav::Params& P) {
+  const size_t smem = trav::sparse_smem(P.k);
+  if (smem > 200 * 1024) return TKNN_EINVAL;  // caller falls back to the cooperative kernel
+  const unsigned grid = (unsigned)((P.n_active + trav::SPARSE_THREADS - 1) / trav::SPARSE_THREADS);
+  if (c->counters) {
+    auto kern = trav::traverse_sparse_kernel<true>;
+    TK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, trav::SPARSE_THREADS, smem, c->stream>>>(P);
+  } else {
+    auto kern = trav::traverse_sparse_kernel<false>;
+    TK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, trav::SPARSE_THREADS, smem, c->stream>>>(P);
   }
   TK_CUDA(c, cudaGetLastError());
   return TKNN_OK;
@@ -240,7 +263,12 @@ int run_rounds(tknn_ctx* c, const Job& job, int* launches_io) {
     TK_CUDA(c, cudaMemsetAsync(sc + SC_GROUP_COUNTER, 0, sizeof(uint32_t), c->stream));
     const bool timed = job.record_stats && round < TKNN_MAX_ROUNDS;
     if (timed) TK_CUDA(c, cudaEventRecord(c->round_ev[4 * round + 2], c->stream));
-    TK_TRY(launch_traverse<trav::MODE_KNN>(c, P));
+    // sparse remainder (< 1/sparse_divisor of the round-1 queries, taken from a queue): one thread per query
+    const bool sparse = trav::sparse_smem(job.k) <= 200 * 1024 &&
+                        (job.force_sparse || (c->sparse_divisor > 0 && queue != nullptr && round > 0 &&
+                                              active * (uint64_t)c->sparse_divisor <= n0));
+    if (sparse) TK_TRY(launch_traverse_sparse(c, P));
+    else TK_TRY(launch_traverse<trav::MODE_KNN>(c, P));
     if (timed) TK_CUDA(c, cudaEventRecord(c->round_ev[4 * round + 3], c->stream));
     ++launches;
 
@@ -275,17 +303,10 @@ int run_rounds(tknn_ctx* c, const Job& job, int* launches_io) {
 // Sampled k-th-neighbour distance -> start radius (role of Util/random_sample.py:5-32).
 int estimate_radius(tknn_ctx* c, const float4* queries, uint64_t q_begin, uint64_t nq, const int32_t* self_ids,
                     int self_is_row, int k, float* out, int* launches) {
-  const uint64_t groups = (nq + 31) / 32;
-  const uint64_t sg = std::min<uint64_t>((uint64_t)std::max(1, c->sample_groups), groups);
+  const uint64_t want = std::min<uint64_t>((uint64_t)std::max(1, c->sample_groups) * 32, nq);
   std::vector<uint32_t> q;
-  q.reserve(sg * 32);
-  for (uint64_t s = 0; s < sg; ++s) {
-    const uint64_t g = (groups * s) / sg;
-    for (int l = 0; l < 32; ++l) {
-      const uint64_t pos = g * 32 + l;
-      if (pos < nq) q.push_back((uint32_t)(q_begin + pos));
-    }
-  }
+  q.reserve(want);
+  for (uint64_t s = 0; s < want; ++s) q.push_back((uint32_t)(q_begin + (nq * s) / want));  // evenly spaced, ascending
   const size_t m = q.size();
   TK_TRY(ensure(c, c->sample, m * sizeof(uint32_t) + m * (size_t)k * (sizeof(int32_t) + sizeof(float))));
   uint32_t* dq = c->sample.as<uint32_t>();
@@ -306,6 +327,7 @@ int estimate_radius(tknn_ctx* c, const float4* queries, uint64_t q_begin, uint64
   job.idx_out = di;
   job.dist_out = dd;
   job.record_stats = false;
+  job.force_sparse = true;
   const int saved = c->counters;
   c->counters = 0;
   int rc = run_rounds(c, job, launches);
@@ -539,6 +561,10 @@ int tknn_set_option(tknn_ctx* c, int key, int64_t value) {
       return TKNN_OK;
     case TKNN_OPT_SQUARED_DIST: c->squared = value ? 1 : 0; return TKNN_OK;
     case TKNN_OPT_KEEP_SCRATCH: c->keep_scratch = value ? 1 : 0; return TKNN_OK;
+    case TKNN_OPT_SPARSE_DIVISOR:
+      if (value < 0 || value > 1000000) return fail(c, TKNN_EINVAL, "sparse divisor outside [0, 1e6]");
+      c->sparse_divisor = (int)value;
+      return TKNN_OK;
     case TKNN_OPT_RADIUS_QUANTILE:
       if (value < 0 || value > 1000) return fail(c, TKNN_EINVAL, "radius quantile outside [0, 1000] per mille");
       c->radius_quantile = (int)value;

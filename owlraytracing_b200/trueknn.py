@@ -95,7 +95,7 @@ class TrueKNN:
         "leaf_size": _lib.OPT_LEAF_SIZE, "counters": _lib.OPT_COUNTERS, "leaf_policy": _lib.OPT_LEAF_POLICY,
         "sample_groups": _lib.OPT_SAMPLE_GROUPS, "blocks_per_sm": _lib.OPT_BLOCKS_PER_SM,
         "squared_dist": _lib.OPT_SQUARED_DIST, "radius_quantile": _lib.OPT_RADIUS_QUANTILE,
-        "keep_scratch": _lib.OPT_KEEP_SCRATCH,
+        "keep_scratch": _lib.OPT_KEEP_SCRATCH, "sparse_divisor": _lib.OPT_SPARSE_DIVISOR,
     }
 
     def set_option(self, name: str, value: int):
