@@ -145,11 +145,12 @@ TKNN_API int tknn_search_shard(tknn_ctx* ctx, int k, float start_radius, int sha
 TKNN_API uint64_t tknn_shard_capacity(uint64_t n, int n_shards);
 
 /* Separate query set on the built BVH.  queries: nq rows; self_ids (may be
- * NULL) names the data index to exclude per query (-1: none); init_radius (may be NULL): per-query
- * closed search radius (used by the point-partitioned driver for boundary queries).
- * Output rows follow the query order. */
+ * NULL) names the data index to exclude per query (-1: none); init_radius2 (may be NULL): per-query
+ * cap on the SQUARED distance, closed (d2 <= cap; negative = no cap) — squared so that the
+ * point-partitioned driver can pass a k-th-neighbour d2 bit-exactly for its boundary queries.
+ * Output rows follow the query order; rows with fewer than k neighbours end in -1 / FLT_MAX. */
 TKNN_API int tknn_query(tknn_ctx* ctx, const float* queries, uint64_t nq, int dim, int stride_floats,
-                        const int32_t* self_ids, const float* init_radius, int k, float start_radius,
+                        const int32_t* self_ids, const float* init_radius2, int k, float start_radius,
                         int32_t* idx_out, float* dist_out);
 
 /* Fixed-radius neighbour count per point (closed ball, self excluded) on the same traversal
@@ -169,7 +170,8 @@ TKNN_API int tknn_brute_force(tknn_ctx* ctx, const int32_t* query_ids, uint64_t 
  * of k (idx, d2) pairs (layout [parts][nq][k], a list ends at its first -1 index, duplicates by
  * index removed) into one list of k.  d2_parts holds SQUARED distances (produced with
  * TKNN_OPT_SQUARED_DIST = 1: sqrtf is not injective, so only d2 gives the exact order); dist_out
- * receives sqrtf(d2).  Used by the point-partitioned driver. */
+ * receives sqrtf(d2), or d2 again while TKNN_OPT_SQUARED_DIST is set (chained merges).  Used by the
+ * point-partitioned driver. */
 TKNN_API int tknn_merge_topk(tknn_ctx* ctx, const int32_t* idx_parts, const float* d2_parts, int parts, uint64_t nq,
                              int k, int32_t* idx_out, float* dist_out);
 
@@ -186,6 +188,12 @@ TKNN_API int tknn_sort_pairs(tknn_ctx* ctx, uint64_t* keys, uint32_t* values, ui
 /* Copies of the built BVH: nodes (n_nodes x 16 words), sorted points
  * (n x float4: x, y, z, original index bits), leaf starts (n_leaves + 1).  NULL pointers skipped. */
 TKNN_API int tknn_get_bvh(const tknn_ctx* ctx, void* nodes_out, void* points_out, uint32_t* leaf_start_out);
+
+/* 63-bit Morton codes of n points on the cubic grid spanning box = {lo.xyz, hi.xyz} (the same code
+ * the builder sorts by); the point-partitioned driver uses it with the GLOBAL box to assign Morton
+ * ranges to ranks.  Device or host arrays. */
+TKNN_API int tknn_morton_codes(tknn_ctx* ctx, const float* xyz, uint64_t n, int dim, int stride_floats,
+                               const float* box6, uint64_t* codes_out);
 
 /* Synthetic clouds generated on the device by the stateless hash of SURVEY.md §8d:
  * u(i,a) = (mix64(seed ^ ((3i+a) * 0x9E3779B97F4A7C15)) >> 40) * 2^-24.  Writes n rows of xyz

@@ -81,6 +81,10 @@ TKO_INLINE void tko_list_insert(uint64_t* list, int* cnt, int k, uint64_t key) {
   *cnt = c + 1;
 }
 
+static int tko_squared_output = 0; /* 1: report d2 instead of sqrtf(d2) (stand-in engine of the multi-GPU host tests) */
+
+TKO_API void tko_set_squared_output(int on) { tko_squared_output = on ? 1 : 0; }
+
 TKO_INLINE void tko_list_emit(const uint64_t* list, int cnt, int k, int32_t* idx_out, float* dist_out) {
   for (int i = 0; i < k; ++i) {
     if (i < cnt) {
@@ -88,7 +92,7 @@ TKO_INLINE void tko_list_emit(const uint64_t* list, int cnt, int k, int32_t* idx
       float d2;
       memcpy(&d2, &b, 4);
       idx_out[i] = (int32_t)(uint32_t)(list[i] & 0xffffffffu);
-      dist_out[i] = sqrtf(d2);
+      dist_out[i] = tko_squared_output ? d2 : sqrtf(d2);
     } else { /* unfilled-slot sentinels, hostCode.cpp:129 */
       idx_out[i] = -1;
       dist_out[i] = FLT_MAX;
@@ -115,7 +119,7 @@ TKO_API float tko_dist2(const float* q, const float* p) { return tko_d2(q[0], q[
  * ---------------------------------------------------------------------------------------- */
 TKO_CLONES
 TKO_API int tko_knn_brute_queries(const float* xyz, int64_t n, const float* q, int64_t nq, const int32_t* self_ids,
-                                  int k, float radius2, int32_t* idx_out, float* dist_out) {
+                                  int k, float radius2, const float* caps2, int32_t* idx_out, float* dist_out) {
   if (!xyz || !q || n < 0 || nq < 0 || k <= 0) return 1;
 #pragma omp parallel
   {
@@ -126,6 +130,7 @@ TKO_API int tko_knn_brute_queries(const float* xyz, int64_t n, const float* q, i
       const int64_t self = self_ids ? self_ids[i] : (q == xyz ? i : -1);
       int cnt = 0;
       float worst = radius2;
+      if (caps2 && caps2[i] >= 0.0f && caps2[i] < worst) worst = caps2[i]; /* per-query closed cap on d2 */
       for (int64_t j = 0; j < n; ++j) {
         float d2 = tko_d2(qx, qy, qz, xyz[3 * j], xyz[3 * j + 1], xyz[3 * j + 2]);
         if (d2 > worst || j == self) continue;
@@ -143,7 +148,7 @@ TKO_API int tko_knn_brute_queries(const float* xyz, int64_t n, const float* q, i
 }
 
 TKO_API int tko_knn_brute(const float* xyz, int64_t n, int k, int32_t* idx_out, float* dist_out) {
-  return tko_knn_brute_queries(xyz, n, xyz, n, NULL, k, INFINITY, idx_out, dist_out);
+  return tko_knn_brute_queries(xyz, n, xyz, n, NULL, k, INFINITY, NULL, idx_out, dist_out);
 }
 
 /* ------------------------------------------------------------------------------------------

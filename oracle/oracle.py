@@ -37,7 +37,8 @@ def lib() -> C.CDLL:
         L.tko_dist2.restype = C.c_float
         L.tko_dist2.argtypes = [f32p, f32p]
         L.tko_knn_brute.argtypes = [f32p, C.c_int64, C.c_int, i32p, f32p]
-        L.tko_knn_brute_queries.argtypes = [f32p, C.c_int64, f32p, C.c_int64, i32p, C.c_int, C.c_float, i32p, f32p]
+        L.tko_knn_brute_queries.argtypes = [f32p, C.c_int64, f32p, C.c_int64, i32p, C.c_int, C.c_float, f32p, i32p, f32p]
+        L.tko_set_squared_output.argtypes = [C.c_int]
         L.tko_knn_kdtree.argtypes = [f32p, C.c_int64, C.c_int, i32p, f32p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.tko_kdtree_build.restype = C.c_void_p
         L.tko_kdtree_build.argtypes = [f32p, C.c_int64, C.c_int]
@@ -80,7 +81,12 @@ def knn_brute(xyz, k):
     return idx, dist
 
 
-def knn_brute_queries(xyz, queries, k, self_ids=None, radius2=np.inf):
+def set_squared_output(on: bool):
+    """Report d2 instead of sqrtf(d2) (used by the stand-in engine of the multi-GPU host tests)."""
+    lib().tko_set_squared_output(1 if on else 0)
+
+
+def knn_brute_queries(xyz, queries, k, self_ids=None, radius2=np.inf, caps2=None):
     xyz = _f32(xyz).reshape(-1, 3)
     q = _f32(queries).reshape(-1, 3)
     nq = q.shape[0]
@@ -91,8 +97,9 @@ def knn_brute_queries(xyz, queries, k, self_ids=None, radius2=np.inf):
         sid = np.full(nq, -1, np.int32)
     idx = np.empty((nq, k), np.int32)
     dist = np.empty((nq, k), np.float32)
+    caps = _f32(caps2) if caps2 is not None else None
     rc = lib().tko_knn_brute_queries(_p(xyz, C.c_float), xyz.shape[0], _p(q, C.c_float), nq, _p(sid, C.c_int32), k,
-                                     C.c_float(radius2), _p(idx, C.c_int32), _p(dist, C.c_float))
+                                     C.c_float(radius2), _p(caps, C.c_float), _p(idx, C.c_int32), _p(dist, C.c_float))
     assert rc == 0
     return idx, dist
 

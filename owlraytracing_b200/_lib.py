@@ -73,7 +73,7 @@ EXPORTS = [
     "tknn_create", "tknn_destroy", "tknn_set_stream", "tknn_set_option", "tknn_build", "tknn_search",
     "tknn_search_shard", "tknn_shard_capacity", "tknn_query", "tknn_range_count", "tknn_estimate_start_radius",
     "tknn_brute_force", "tknn_merge_topk", "tknn_get_stats", "tknn_last_error", "tknn_version", "tknn_sort_pairs",
-    "tknn_get_bvh", "tknn_generate_uniform", "tknn_measure_bandwidth",
+    "tknn_get_bvh", "tknn_generate_uniform", "tknn_measure_bandwidth", "tknn_morton_codes",
 ]
 
 _lib = None
@@ -111,6 +111,7 @@ def load() -> C.CDLL:
     L.tknn_sort_pairs.argtypes = [vp, vp, vp, u64]
     L.tknn_get_bvh.argtypes = [vp, vp, vp, vp]
     L.tknn_generate_uniform.argtypes = [vp, u64, u64, u64, vp]
+    L.tknn_morton_codes.argtypes = [vp, vp, u64, C.c_int, C.c_int, vp, vp]
     L.tknn_measure_bandwidth.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int),
                                          C.POINTER(u64)]
     _lib = L

@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(32) merge_keys_kernel(const uint64_t* __restri
 // be the (d2, index) order.  Duplicates by index are dropped; the output distance is sqrtf(d2).
 __global__ void __launch_bounds__(32) merge_lists_kernel(const int32_t* __restrict__ idx_parts,
                                                          const float* __restrict__ dist_parts, int parts, uint32_t nq, int k,
-                                                         int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+                                                         int squared, int32_t* __restrict__ idx_out,
+                                                         float* __restrict__ dist_out) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x;
   uint64_t* H = reinterpret_cast<uint64_t*>(smem) + lane;
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(32) merge_lists_kernel(const int32_t* __restri
   for (int i = cnt - 1; i >= 0; --i) {
     const uint64_t top = H[0];
     io[i] = key_idx(top);
-    dd[i] = __fsqrt_rn(key_d2(top));
+    dd[i] = squared ? key_d2(top) : __fsqrt_rn(key_d2(top));
     if (i > 0) trav::heap_sift_root(H, i, H[i * 32]);
   }
 }
@@ -164,12 +165,12 @@ __global__ void __launch_bounds__(256) gather_i32_kernel(const int32_t* __restri
   const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
   if (i < n) out[i] = in[order[i]];
 }
-__global__ void __launch_bounds__(256) gather_r2_kernel(const float* __restrict__ radius, const uint32_t* __restrict__ order,
+__global__ void __launch_bounds__(256) gather_r2_kernel(const float* __restrict__ radius2, const uint32_t* __restrict__ order,
                                                         uint64_t n, float* __restrict__ r2_out) {
   const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
   if (i < n) {
-    const float r = radius[order[i]];
-    r2_out[i] = r >= 0.0f ? __fmul_rn(r, r) : INFINITY;  // negative = no cap
+    const float r2 = radius2[order[i]];
+    r2_out[i] = r2 >= 0.0f ? r2 : INFINITY;  // negative = no cap
   }
 }
 

@@ -774,7 +774,7 @@ int tknn_estimate_start_radius(tknn_ctx* c, int k, float* radius_out) {
 }
 
 int tknn_query(tknn_ctx* c, const float* queries, uint64_t nq, int dim, int stride_floats, const int32_t* self_ids,
-               const float* init_radius, int k, float start_radius, int32_t* idx_out, float* dist_out) {
+               const float* init_radius2, int k, float start_radius, int32_t* idx_out, float* dist_out) {
   TK_TRY(check_ctx(c));
   if (c->n == 0) return fail(c, TKNN_ESTATE, "tknn_query before tknn_build");
   if (!queries && nq) return fail(c, TKNN_EINVAL, "null query array");
@@ -817,10 +817,10 @@ int tknn_query(tknn_ctx* c, const float* queries, uint64_t nq, int dim, int stri
     TK_BC(cudaMemcpyAsync(sid_stage.p, self_ids, nq * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     d_sid = sid_stage.as<int32_t>();
   }
-  const float* d_rad = init_radius;
-  if (init_radius && !is_device_ptr(init_radius)) {
+  const float* d_rad = init_radius2;
+  if (init_radius2 && !is_device_ptr(init_radius2)) {
     TK_B(ensure(c, rad_stage, nq * sizeof(float)));
-    TK_BC(cudaMemcpyAsync(rad_stage.p, init_radius, nq * sizeof(float), cudaMemcpyHostToDevice, st));
+    TK_BC(cudaMemcpyAsync(rad_stage.p, init_radius2, nq * sizeof(float), cudaMemcpyHostToDevice, st));
     d_rad = rad_stage.as<float>();
   }
   // Morton-sort the queries on the DATA's grid so that groups of 32 are spatially coherent
@@ -867,7 +867,7 @@ int tknn_query(tknn_ctx* c, const float* queries, uint64_t nq, int dim, int stri
   // a query set can hold fewer than k reachable neighbours only through self exclusion / radius caps
   const bool may_underfill = (uint64_t)k > c->n - (self_ids ? 1 : 0);
   if (!(r0 > 0.0f)) {
-    if (init_radius || may_underfill) r0 = INFINITY;
+    if (init_radius2 || may_underfill) r0 = INFINITY;
     else TK_B(estimate_radius(c, qpts.as<float4>(), 0, nq, d_sid_sorted, 0, k, &r0, &launches));
   }
   TK_BC(cudaEventRecord(c->ev[1], st));
@@ -1026,7 +1026,7 @@ int tknn_merge_topk(tknn_ctx* c, const int32_t* idx_parts, const float* d2_parts
   const size_t smem = (size_t)k * 32 * sizeof(uint64_t);
   TK_CUDA(c, cudaFuncSetAttribute(brute::merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   brute::merge_lists_kernel<<<(unsigned)((nq + 31) / 32), 32, smem, c->stream>>>(idx_parts, d2_parts, parts, (uint32_t)nq, k,
-                                                                               idx_out, dist_out);
+                                                                               c->squared, idx_out, dist_out);
   TK_CUDA(c, cudaGetLastError());
   TK_CUDA(c, cudaStreamSynchronize(c->stream));
   return TKNN_OK;
@@ -1080,6 +1080,53 @@ int tknn_get_bvh(const tknn_ctx* c, void* nodes_out, void* points_out, uint32_t*
   if (leaf_start_out &&
       cudaMemcpy(leaf_start_out, c->leaf_start.p, (size_t)(c->n_leaves + 1) * sizeof(uint32_t), cudaMemcpyDefault) != cudaSuccess)
     return TKNN_ECUDA;
+  return TKNN_OK;
+}
+
+int tknn_morton_codes(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int stride_floats, const float* box6,
+                      uint64_t* codes_out) {
+  TK_TRY(check_ctx(c));
+  if (n == 0) return TKNN_OK;
+  if (!xyz || !box6 || !codes_out) return fail(c, TKNN_EINVAL, "null array");
+  if (dim != 2 && dim != 3) return fail(c, TKNN_EINVAL, "dim = %d (must be 2 or 3)", dim);
+  if (stride_floats < dim) return fail(c, TKNN_EINVAL, "stride %d < dim %d", stride_floats, dim);
+  ScopedDevice sd(c->device);
+  cudaStream_t st = c->stream;
+  float hbox[6];
+  if (is_device_ptr(box6)) {
+    TK_CUDA(c, cudaMemcpyAsync(hbox, box6, sizeof(hbox), cudaMemcpyDeviceToHost, st));
+    TK_CUDA(c, cudaStreamSynchronize(st));
+  } else {
+    std::memcpy(hbox, box6, sizeof(hbox));
+  }
+  // same order-preserving encoding the builder's bounds kernel produces
+  auto enc = [](float f) { uint32_t b; std::memcpy(&b, &f, 4); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); };
+  uint32_t ob[8] = {enc(hbox[0]), enc(hbox[1]), enc(hbox[2]), enc(hbox[3]), enc(hbox[4]), enc(hbox[5]), 0u, 0u};
+  DevBuf in, keys, vals, dob;
+  auto cleanup = [&]() { for (DevBuf* b : {&in, &keys, &vals, &dob}) release(*b); };
+#define TK_B(expr) do { int rc_ = (expr); if (rc_ != TKNN_OK) { cleanup(); return rc_; } } while (0)
+#define TK_BC(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cudaGetLastError(); cleanup(); \
+    return fail(c, e_ == cudaErrorMemoryAllocation ? TKNN_ENOMEM : TKNN_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); } } while (0)
+  const float* d_xyz = xyz;
+  if (!is_device_ptr(xyz)) {
+    TK_B(ensure(c, in, (size_t)n * stride_floats * sizeof(float)));
+    TK_BC(cudaMemcpyAsync(in.p, xyz, (size_t)n * stride_floats * sizeof(float), cudaMemcpyHostToDevice, st));
+    d_xyz = in.as<float>();
+  }
+  const bool out_dev = is_device_ptr(codes_out);
+  uint64_t* d_keys = codes_out;
+  if (!out_dev) { TK_B(ensure(c, keys, n * sizeof(uint64_t))); d_keys = keys.as<uint64_t>(); }
+  TK_B(ensure(c, vals, n * sizeof(uint32_t)));
+  TK_B(ensure(c, dob, sizeof(ob)));
+  TK_BC(cudaMemcpyAsync(dob.p, ob, sizeof(ob), cudaMemcpyHostToDevice, st));
+  lbvh::morton_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, n, dim, stride_floats, dob.as<uint32_t>(),
+                                                                             d_keys, vals.as<uint32_t>());
+  TK_BC(cudaGetLastError());
+  if (!out_dev) TK_BC(cudaMemcpyAsync(codes_out, d_keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  TK_BC(cudaStreamSynchronize(st));
+  cleanup();
+#undef TK_B
+#undef TK_BC
   return TKNN_OK;
 }
 

@@ -170,8 +170,9 @@ class TrueKNN:
         m = int(m.value)
         return qid[:m], idx[:m], dist[:m]
 
-    def query(self, queries, k: int, self_ids=None, init_radius=None, start_radius: float = 0.0, dim: int | None = None):
-        """kNN of a separate query set against the built BVH; rows follow the query order."""
+    def query(self, queries, k: int, self_ids=None, init_radius2=None, start_radius: float = 0.0, dim: int | None = None):
+        """kNN of a separate query set against the built BVH; rows follow the query order.
+        init_radius2: optional per-query cap on the squared distance (closed; negative = none)."""
         if not _is_tensor(queries):
             queries = np.ascontiguousarray(queries, dtype=np.float32)
         _check_dtype(queries, np.float32, "queries")
@@ -180,11 +181,11 @@ class TrueKNN:
             dim = min(stride, 3)
         if self_ids is not None and not _is_tensor(self_ids):
             self_ids = np.ascontiguousarray(self_ids, dtype=np.int32)
-        if init_radius is not None and not _is_tensor(init_radius):
-            init_radius = np.ascontiguousarray(init_radius, dtype=np.float32)
+        if init_radius2 is not None and not _is_tensor(init_radius2):
+            init_radius2 = np.ascontiguousarray(init_radius2, dtype=np.float32)
         idx = self._out(queries, nq, k, np.int32)
         dist = self._out(queries, nq, k, np.float32)
-        self._check(self._L.tknn_query(self._h, _ptr(queries), nq, int(dim), stride, _ptr(self_ids), _ptr(init_radius), int(k),
+        self._check(self._L.tknn_query(self._h, _ptr(queries), nq, int(dim), stride, _ptr(self_ids), _ptr(init_radius2), int(k),
                                        C.c_float(start_radius), _ptr(idx), _ptr(dist)))
         return idx, dist
 
@@ -236,6 +237,24 @@ class TrueKNN:
         leaf_start = np.empty((st["n_leaves"] + 1,), np.uint32)
         self._check(self._L.tknn_get_bvh(self._h, _ptr(nodes), _ptr(pts), _ptr(leaf_start)))
         return nodes, pts, leaf_start
+
+    def morton_codes(self, points, box6, dim: int | None = None):
+        """63-bit Morton codes on the cubic grid over `box6` = (lo.xyz, hi.xyz); int64/uint64 [n]."""
+        if not _is_tensor(points):
+            points = np.ascontiguousarray(points, dtype=np.float32)
+        n, stride = int(points.shape[0]), int(points.shape[1])
+        if dim is None:
+            dim = min(stride, 3)
+        if _is_tensor(points):
+            import torch
+
+            out = torch.empty((n,), dtype=torch.int64, device=points.device)
+            box = torch.as_tensor(box6, dtype=torch.float32).cpu().contiguous().numpy()
+        else:
+            out = np.empty((n,), np.uint64)
+            box = np.ascontiguousarray(box6, dtype=np.float32)
+        self._check(self._L.tknn_morton_codes(self._h, _ptr(points), n, int(dim), stride, _ptr(box), _ptr(out)))
+        return out
 
     def generate_uniform(self, seed: int, first: int, n: int, out=None):
         if out is None:

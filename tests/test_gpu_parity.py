@@ -175,10 +175,10 @@ def test_separate_query_set(knn, oracle):
     full = oracle.knn_kdtree(x, 9)
     assert_knn_equal(idx, dist, full[0][sub], full[1][sub], "query with self ids")
     # per-query radius caps (boundary queries of the point-partitioned driver)
-    rad = rng.random(q.shape[0], dtype=np.float32) * 0.05
-    idx, dist = knn.query(q, 9, init_radius=rad)
+    rad2 = (rng.random(q.shape[0], dtype=np.float32) * 0.05) ** 2
+    idx, dist = knn.query(q, 9, init_radius2=rad2)
     for i in range(0, q.shape[0], 50):
-        ri, rd = oracle.knn_brute_queries(x, q[i:i + 1], 9, radius2=np.float32(rad[i]) * np.float32(rad[i]))
+        ri, rd = oracle.knn_brute_queries(x, q[i:i + 1], 9, radius2=rad2[i])
         assert (idx[i] == ri[0]).all() and (dist[i] == rd[0]).all()
 
 
@@ -253,3 +253,51 @@ def test_torch_device_tensors(knn, oracle):
     idx, dist = knn.build(xd).search(10)
     assert idx.is_cuda and dist.is_cuda
     assert_knn_equal(idx.cpu().numpy(), dist.cpu().numpy(), *oracle.knn_kdtree(x, 10), "torch tensors")
+
+
+def test_merge_topk_and_morton_codes_match_the_cpu_stand_in(knn):
+    """The two C-ABI helpers of the point-partitioned driver against the numpy stand-in the gloo tests use."""
+    import torch
+
+    from cpu_engine import CpuEngine
+
+    rng = np.random.default_rng(4)
+    x = datasets.lidar_like(20_000, seed=9)
+    box = np.concatenate([x.min(0), x.max(0)]).astype(np.float32)
+    assert (knn.morton_codes(x, box).astype(np.int64) == CpuEngine().morton_codes(x, box).numpy()).all()
+    codes_dev = knn.morton_codes(torch.from_numpy(x).cuda(), box)
+    assert (codes_dev.cpu().numpy() == CpuEngine().morton_codes(x, box).numpy()).all()
+    # partial lists with ties, duplicates across parts and short lists
+    parts, nq, k = 3, 500, 7
+    ip = rng.integers(0, 40, (parts, nq, k)).astype(np.int32)
+    dp = (rng.integers(0, 6, (parts, nq, k)) * 0.25).astype(np.float32)
+    # a point has one distance: make d2 a function of the index so that duplicates agree
+    dp = ((ip % 6) * 0.25).astype(np.float32)
+    order = np.lexsort((ip, dp), axis=-1)  # ascending (d2, idx) inside each list
+    ip, dp = np.take_along_axis(ip, order, -1), np.take_along_axis(dp, order, -1)
+    for s in range(parts):  # remove in-list duplicates, pad with -1
+        for q in range(nq):
+            _, first = np.unique(ip[s, q], return_index=True)
+            keep = np.sort(first)
+            m = keep.size
+            ip[s, q, :m], dp[s, q, :m] = ip[s, q, keep], dp[s, q, keep]
+            ip[s, q, m:], dp[s, q, m:] = -1, np.finfo(np.float32).max
+    ref_i, ref_d = CpuEngine().merge_topk(ip, dp)
+    gi, gd = knn.merge_topk(torch.from_numpy(ip).cuda(), torch.from_numpy(dp).cuda())
+    assert (gi.cpu().numpy() == ref_i.numpy()).all()
+    assert np.allclose(gd.cpu().numpy(), ref_d.numpy(), rtol=1e-6, atol=0)
+
+
+def test_point_partitioned_driver_single_rank(knn, oracle):
+    """world_size 1 on the GPU: the partitioned driver degenerates to local search with global ids."""
+    import torch
+
+    from owlraytracing_b200.partitioned import PartitionedTrueKNN
+
+    x = datasets.uniform(30_000, seed=8)
+    drv = PartitionedTrueKNN(engine=knn).build(torch.from_numpy(x).cuda(), 1000)
+    gid, idx, dist = drv.search(10)
+    ref_i, ref_d = oracle.knn_kdtree(x, 10)
+    assert (gid.cpu().numpy() == np.arange(1000, 31_000)).all()
+    assert (idx.cpu().numpy() == ref_i + 1000).all()
+    assert np.allclose(dist.cpu().numpy(), ref_d, rtol=1e-6, atol=0)
