@@ -208,7 +208,7 @@ def run_gpu(args):
     n_points = cfg["n"] * world if weak_grow else cfg["n"]
     if args.points:
         n_points = args.points
-    scaling = "weak" if (weak_grow or world == 1) else cfg["scaling"]
+    scaling = cfg["scaling"] if args.workload != "cfg2" else "weak"
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:

@@ -200,6 +200,14 @@ TKNN_API int tknn_morton_codes(tknn_ctx* ctx, const float* xyz, uint64_t n, int 
  * for indices [first, first+n) to a DEVICE or HOST array. */
 TKNN_API int tknn_generate_uniform(tknn_ctx* ctx, uint64_t seed, uint64_t first, uint64_t n, float* xyz_out);
 
+/* Point-file ingest and neighbour writer (host only, no CUDA).
+ * tknn_read_points: the sample's file grammar (hostCode.cpp:83-124), mmap + parallel parse; names
+ * ending in ".f32" are raw little-endian float32 rows of `dim`.  xyz_out: n_cap rows of 3 floats.
+ * tknn_write_neighbours: `query,neighbourIndex,distance` lines (the dump commented out at
+ * hostCode.cpp:312-319), or raw arrays (path + ".idx.i32" / ".dist.f32") when binary != 0. */
+TKNN_API int tknn_read_points(const char* path, uint64_t n, int dim, float* xyz_out, uint64_t n_cap, uint64_t* n_out);
+TKNN_API int tknn_write_neighbours(const char* path, const int32_t* idx, const float* dist, uint64_t n, int k, int binary);
+
 /* Device properties the roofline needs: SM count, L2 bytes, and a measured L2 / HBM read
  * bandwidth (GB/s) from a short read loop over an L2-resident / HBM-sized buffer. */
 TKNN_API int tknn_measure_bandwidth(tknn_ctx* ctx, double* l2_gbs, double* hbm_gbs, int* sm_count, uint64_t* l2_bytes);

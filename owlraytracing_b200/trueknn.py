@@ -314,6 +314,29 @@ def read_points(path: str, n: int, dim: int) -> np.ndarray:
     return np.ascontiguousarray(pts, dtype=np.float32)
 
 
+def read_points_fast(path: str, n: int, dim: int) -> np.ndarray:
+    """Same grammar as read_points, parsed in parallel by libtrueknn (tknn_read_points)."""
+    L = _lib.load()
+    cap = int(n) + 8
+    out = np.empty((cap, 3), np.float32)
+    m = C.c_uint64(0)
+    rc = L.tknn_read_points(path.encode(), int(n), int(dim), C.c_void_p(out.ctypes.data), cap, C.byref(m))
+    if rc != _lib.OK:
+        raise ValueError(f"tknn_read_points({path!r}) failed with {_lib.ERROR_NAMES.get(rc, rc)}")
+    return np.ascontiguousarray(out[: int(m.value)])
+
+
+def write_neighbours(path: str, idx: np.ndarray, dist: np.ndarray, binary: bool = False):
+    """`query,neighbourIndex,distance` lines (hostCode.cpp:316, commented out in the reference) or raw arrays."""
+    L = _lib.load()
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    dist = np.ascontiguousarray(dist, dtype=np.float32)
+    rc = L.tknn_write_neighbours(path.encode(), C.c_void_p(idx.ctypes.data), C.c_void_p(dist.ctypes.data), idx.shape[0],
+                                 idx.shape[1], 1 if binary else 0)
+    if rc != _lib.OK:
+        raise OSError(f"tknn_write_neighbours({path!r}) failed")
+
+
 def run_sample(argv: list[str], device: int = 0, neighbours_path: str | None = None) -> dict:
     """`sample01-trueknn file n dim start_radius k outfile` (samples/s01-trueknn/README.md:7-14).
 
@@ -323,7 +346,7 @@ def run_sample(argv: list[str], device: int = 0, neighbours_path: str | None = N
     if len(argv) != 6:
         raise SystemExit("usage: trueknn <file> <n> <dim> <start radius> <k> <output file>")
     path, n, dim, r0, k, outfile = argv[0], int(argv[1]), int(argv[2]), float(argv[3]), int(argv[4]), argv[5]
-    pts = read_points(path, n, dim)
+    pts = read_points_fast(path, n, dim)
     with TrueKNN(device) as t:
         t0 = time.perf_counter()
         t.build(pts, dim=3)
@@ -335,9 +358,6 @@ def run_sample(argv: list[str], device: int = 0, neighbours_path: str | None = N
     with open(outfile, "a") as f:
         f.write(f"{total}\n")
     if neighbours_path:
-        q = np.repeat(np.arange(idx.shape[0]), k)
-        with open(neighbours_path, "w") as f:
-            for a, b, d in zip(q, idx.reshape(-1), dist.reshape(-1)):
-                f.write(f"{a},{b},{d:.9g}\n")
+        write_neighbours(neighbours_path, idx, dist)
     return {"build_s": t1 - t0, "knn_s": t2 - t1, "total_s": total, "rounds": st["rounds"], "idx": idx, "dist": dist,
             "stats": st}

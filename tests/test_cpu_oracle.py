@@ -199,3 +199,48 @@ def test_product_code_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "liboracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_fast_ingest_matches_grammar_and_writer_round_trips(oracle, tmp_path):
+    """tknn_read_points (mmap + parallel parse) against the reference-grammar restatement, and the
+    neighbour writer in the format the reference leaves commented out (hostCode.cpp:316)."""
+    from owlraytracing_b200 import read_points_fast, write_neighbours
+
+    rng = np.random.default_rng(3)
+    x = (rng.random((200_000, 3)) * 200 - 100).astype(np.float32)
+    lines = []
+    for i, p in enumerate(x):
+        sep = ("," if i % 3 == 0 else " " if i % 3 == 1 else ", ")
+        lines.append(sep.join(repr(float(v)) for v in p))
+    text = ("\n".join(lines) + "\n").encode()
+    path = tmp_path / "big.csv"
+    path.write_bytes(text)
+    for n in (1, 777, 200_000, 300_000):
+        got = read_points_fast(str(path), n, 3)
+        assert got.shape[0] == min(n, 200_000) and (got == x[: got.shape[0]]).all()
+    small = b"1,2,3\n+4 5e0 6\n 7.5, 8e-1 ,9 junk 10\n10,11,12,13\n14,15,16\n"
+    sp = tmp_path / "small.csv"
+    sp.write_bytes(small)
+    for n, dim in ((1, 3), (3, 3), (2, 2), (5, 2), (4, 3)):
+        try:
+            want = oracle.parse_points(small, n, dim)
+        except ValueError:
+            with pytest.raises(ValueError):
+                read_points_fast(str(sp), n, dim)
+            continue
+        got = read_points_fast(str(sp), n, dim)
+        assert got.shape == want.shape and (got == want).all(), (n, dim)
+    b = tmp_path / "pts.f32"
+    x[:1000].tofile(str(b))
+    assert (read_points_fast(str(b), 400, 3) == x[:400]).all()
+    # writer
+    idx = rng.integers(0, 1000, (5000, 4)).astype(np.int32)
+    dist = rng.random((5000, 4)).astype(np.float32)
+    out = tmp_path / "nn.csv"
+    write_neighbours(str(out), idx, dist)
+    back = np.loadtxt(str(out), delimiter=",")
+    assert (back[:, 0] == np.repeat(np.arange(5000), 4)).all()
+    assert (back[:, 1].astype(np.int32) == idx.reshape(-1)).all()
+    assert (back[:, 2].astype(np.float32) == dist.reshape(-1)).all()
+    write_neighbours(str(tmp_path / "nn"), idx, dist, binary=True)
+    assert (np.fromfile(str(tmp_path / "nn.idx.i32"), np.int32).reshape(idx.shape) == idx).all()

@@ -20,48 +20,6 @@
 
 #include "../include/trueknn.h"
 
-namespace {
-
-// hostCode.cpp:83-104: while (getline && count > 0) { stringstream ss(line); while (ss >> f) { push; count--; if (peek == ',') ignore; } }
-bool read_points_text(const std::string& path, long long n, int dim, std::vector<float>& flat) {
-  std::ifstream f(path);
-  if (!f.is_open()) return false;
-  long long owed = n * dim;
-  std::string line;
-  while (owed > 0 && std::getline(f, line)) {
-    const char* p = line.c_str();
-    const char* end = p + line.size();
-    while (p < end) {
-      while (p < end && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\v' || *p == '\f')) ++p;
-      if (p >= end) break;
-      char* q = nullptr;
-      const float v = std::strtof(p, &q);
-      if (q == p) break;  // operator>> fails: the rest of the line is dropped
-      flat.push_back(v);
-      --owed;
-      p = q;
-      if (p < end && *p == ',') ++p;
-    }
-  }
-  return true;
-}
-
-bool read_points_f32(const std::string& path, long long n, int dim, std::vector<float>& flat) {
-  std::ifstream f(path, std::ios::binary);
-  if (!f.is_open()) return false;
-  flat.resize((size_t)n * dim);
-  f.read(reinterpret_cast<char*>(flat.data()), (std::streamsize)(flat.size() * sizeof(float)));
-  flat.resize((size_t)(f.gcount() / (std::streamsize)sizeof(float)) / dim * dim);
-  return true;
-}
-
-bool ends_with(const std::string& s, const char* suf) {
-  const size_t m = std::strlen(suf);
-  return s.size() >= m && s.compare(s.size() - m, m, suf) == 0;
-}
-
-}  // namespace
-
 int main(int ac, char** av) {
   std::vector<std::string> pos;
   std::string neigh_path;
@@ -85,14 +43,15 @@ int main(int ac, char** av) {
   const int k = std::atoi(pos[4].c_str());
   if (dim != 2 && dim != 3) { std::fprintf(stderr, "dimension must be 2 or 3\n"); return 65; }
 
-  std::vector<float> flat;
-  const bool ok = ends_with(path, ".f32") ? read_points_f32(path, n, dim, flat) : read_points_text(path, n, dim, flat);
-  if (!ok) { std::perror("Error open"); return 66; }
-  if (flat.size() % (size_t)dim) {
-    std::fprintf(stderr, "%zu floats is not a multiple of dim=%d (the reference throws std::out_of_range here)\n", flat.size(), dim);
-    return 65;
+  // grammar of hostCode.cpp:83-124 (parallel mmap parser in libtrueknn; rows come back as x, y, z with z = 0 for 2-D)
+  if (n < 0) { std::fprintf(stderr, "number of points must be >= 0\n"); return 65; }
+  std::vector<float> flat((size_t)(n + 8) * 3);
+  uint64_t np = 0;
+  if (tknn_read_points(path.c_str(), (uint64_t)n, dim, flat.data(), (uint64_t)n + 8, &np) != TKNN_OK) {
+    std::fprintf(stderr, "cannot read %s as %d-D points (unreadable, or the float count is not a multiple of dim — "
+                         "the reference throws std::out_of_range there)\n", path.c_str(), dim);
+    return 66;
   }
-  const uint64_t np = flat.size() / (size_t)dim;
   std::cout << " num spheres: " << np << "\n";
 
   tknn_ctx* ctx = nullptr;
@@ -100,7 +59,7 @@ int main(int ac, char** av) {
   if (rc != TKNN_OK) { std::fprintf(stderr, "tknn_create failed (%d): a CUDA sm_100 device is required\n", rc); return 70; }
 
   auto t0 = std::chrono::steady_clock::now();
-  rc = tknn_build(ctx, flat.data(), np, dim, dim);
+  rc = tknn_build(ctx, flat.data(), np, 3, 3);
   auto t1 = std::chrono::steady_clock::now();
   if (rc != TKNN_OK) { std::fprintf(stderr, "tknn_build: %s\n", tknn_last_error(ctx)); tknn_destroy(ctx); return 71; }
   const double build_s = std::chrono::duration<double>(t1 - t0).count();
@@ -129,11 +88,11 @@ int main(int ac, char** av) {
   out << tot << std::endl;
 
   if (!neigh_path.empty()) {
-    std::FILE* f = std::fopen(neigh_path.c_str(), "w");
-    if (!f) { std::perror("Error open"); tknn_destroy(ctx); return 73; }
-    for (uint64_t j = 0; j < np; ++j)
-      for (int i = 0; i < k; ++i) std::fprintf(f, "%llu,%d,%.9g\n", (unsigned long long)j, idx[j * k + i], dist[j * k + i]);
-    std::fclose(f);
+    if (tknn_write_neighbours(neigh_path.c_str(), idx.data(), dist.data(), np, k, 0) != TKNN_OK) {
+      std::perror("Error open");
+      tknn_destroy(ctx);
+      return 73;
+    }
   }
   if (json) {
     std::printf("{\"n\": %llu, \"k\": %d, \"rounds\": %d, \"build_ms\": %.4f, \"search_ms\": %.4f, \"start_radius\": %.9g, "
