@@ -84,28 +84,39 @@ __device__ __forceinline__ void heap_sift_root(uint64_t* H, int size, uint64_t k
 // ---- bounded ASCENDING list of u64 keys in shared memory (slot s of lane l at L[s * 32 + l]) ----
 // Candidates arrive roughly nearest-first, so a new key usually lands near the tail: the backward
 // shift is short, and the list needs no heap-sort at emit time.  Precondition: cnt < k or key < L[k-1].
+// L points at a SENTINEL slot holding 0 (<= every key); entries live in slots 1..k.  The sentinel ends
+// the backward walk without a bounds test, so the loop unrolls to 5 instructions per step.
 __device__ __forceinline__ void list_insert(uint64_t* L, int& cnt, int k, uint64_t key) {
-  uint64_t* p = L + (cnt < k ? cnt : k - 1) * 32;
-  while (p != L) {
-    const uint64_t prev = *(p - 32);
-    if (prev <= key) break;
-    *p = prev;
-    p -= 32;
-  }
-  *p = key;
+  uint64_t* p = L + (cnt < k ? cnt + 1 : k) * 32;  // the slot being filled
   if (cnt < k) ++cnt;
+  for (;;) {
+    const uint64_t a = *(p - 32);
+    if (a <= key) { *p = key; return; }
+    *p = a;
+    const uint64_t b = *(p - 64);
+    if (b <= key) { *(p - 32) = key; return; }
+    *(p - 32) = b;
+    const uint64_t c = *(p - 96);
+    if (c <= key) { *(p - 64) = key; return; }
+    *(p - 64) = c;
+    const uint64_t d = *(p - 128);
+    if (d <= key) { *(p - 96) = key; return; }
+    *(p - 96) = d;
+    p -= 128;
+  }
 }
 
 // k-list policy: ascending list for small k (short shifts, no sort at emit), binary max-heap above
 // (O(log k) per insert; heap-sorted at emit).  Warp-uniform choice.
 constexpr int LIST_MAX_K = 24;
 
-__device__ __forceinline__ uint64_t kl_worst(const uint64_t* H, int k, bool heap) { return heap ? H[0] : H[(k - 1) * 32]; }
+// H = sentinel slot of the lane's region; the heap (large k) uses slots 1..k as its 0-based array
+__device__ __forceinline__ uint64_t kl_worst(const uint64_t* H, int k, bool heap) { return heap ? H[32] : H[k * 32]; }
 
 __device__ __forceinline__ void kl_insert(uint64_t* H, int& cnt, int k, uint64_t key, bool heap) {
   if (heap) {
-    if (cnt < k) heap_push(H, cnt, key);
-    else heap_sift_root(H, k, key);
+    if (cnt < k) heap_push(H + 32, cnt, key);
+    else heap_sift_root(H + 32, k, key);
   } else {
     list_insert(H, cnt, k, key);
   }
@@ -115,15 +126,16 @@ __device__ __forceinline__ void kl_insert(uint64_t* H, int& cnt, int k, uint64_t
 __device__ __forceinline__ void kl_emit(uint64_t* H, int cnt, int k, bool heap, bool squared, int32_t* io, float* dd) {
   for (int i = k - 1; i >= cnt; --i) { io[i] = -1; dd[i] = FLT_MAX; }
   if (heap) {
+    uint64_t* A = H + 32;
     for (int i = cnt - 1; i >= 0; --i) {
-      const uint64_t top = H[0];
+      const uint64_t top = A[0];
       io[i] = key_idx(top);
       dd[i] = squared ? key_d2(top) : __fsqrt_rn(key_d2(top));
-      if (i > 0) heap_sift_root(H, i, H[i * 32]);
+      if (i > 0) heap_sift_root(A, i, A[i * 32]);
     }
   } else {
     for (int i = 0; i < cnt; ++i) {
-      const uint64_t e = H[i * 32];
+      const uint64_t e = H[(i + 1) * 32];
       io[i] = key_idx(e);
       dd[i] = squared ? key_d2(e) : __fsqrt_rn(key_d2(e));
     }
@@ -131,7 +143,7 @@ __device__ __forceinline__ void kl_emit(uint64_t* H, int cnt, int k, bool heap, 
 }
 
 __host__ __device__ inline size_t smem_per_warp(int k) {
-  return (size_t)k * 32 * sizeof(uint64_t) + MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int);
+  return (size_t)(k + 1) * 32 * sizeof(uint64_t) + MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int);
 }
 
 template <int MODE, bool COUNT>
@@ -166,6 +178,7 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
     if (valid && P.query_r2) r2 = fminf(r2, P.query_r2[qpos]);
     float bound = valid ? r2 : -1.0f;  // d2 >= 0 > -1: an idle lane never wants anything
     int cnt = 0;
+    if (MODE == MODE_KNN) H[0] = 0;    // sentinel of this lane's k-list
 
     int sp = 0;
     int node = 0;
@@ -308,14 +321,15 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
 // ------------------------------------------------------------------------------------------------
 constexpr int SPARSE_THREADS = 128;
 
-__host__ __device__ inline size_t sparse_smem(int k) { return (size_t)k * SPARSE_THREADS * sizeof(uint64_t); }
+__host__ __device__ inline size_t sparse_smem(int k) { return (size_t)(k + 1) * SPARSE_THREADS * sizeof(uint64_t); }
 
 template <bool COUNT>
 __global__ void __launch_bounds__(SPARSE_THREADS) traverse_sparse_kernel(const Params P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = P.k;
-  uint64_t* H = reinterpret_cast<uint64_t*>(smem) + (size_t)warp * k * 32 + lane;
+  uint64_t* H = reinterpret_cast<uint64_t*>(smem) + (size_t)warp * (k + 1) * 32 + lane;
+  H[0] = 0;  // sentinel
   const bool heap = k > LIST_MAX_K;
   int stack[STACK_DEPTH];
   unsigned long long c_nodes = 0, c_tests = 0, c_ins = 0;

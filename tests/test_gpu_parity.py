@@ -301,3 +301,32 @@ def test_point_partitioned_driver_single_rank(knn, oracle):
     assert (gid.cpu().numpy() == np.arange(1000, 31_000)).all()
     assert (idx.cpu().numpy() == ref_i + 1000).all()
     assert np.allclose(dist.cpu().numpy(), ref_d, rtol=1e-6, atol=0)
+
+
+def test_cpp_cli_end_to_end(oracle, tmp_path):
+    """tools/trueknn: the sample's six positional arguments (hostCode.cpp:66-73) through the C++ host."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tools", "trueknn")
+    assert os.path.exists(exe), "build it with __graft_entry__.build()"
+    x = datasets.lidar_like(6000, seed=4)
+    csv = tmp_path / "pts.csv"
+    with open(csv, "w") as f:
+        for p in x:
+            f.write(",".join(repr(float(v)) for v in p) + "\n")
+    out, nn = tmp_path / "time.txt", tmp_path / "nn.csv"
+    for r0 in ("0.05", "0"):
+        r = subprocess.run([exe, str(csv), "5000", "3", r0, "7", str(out), "--neighbours", str(nn), "--json"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert "Build time:" in r.stdout and "True KNN time:" in r.stdout and "Total time:" in r.stdout
+        got = np.loadtxt(str(nn), delimiter=",")
+        ref_i, ref_d = oracle.knn_kdtree(x[:5000], 7)   # "always selects first n points" (README.md:10)
+        assert (got[:, 1].astype(np.int32).reshape(5000, 7) == ref_i).all()
+        assert np.allclose(got[:, 2].astype(np.float32).reshape(5000, 7), ref_d, rtol=1e-6, atol=0)
+    assert len(open(out).read().split()) == 2  # one total per run appended (hostCode.cpp:350-356)
+    # k > n - 1: the reference loops forever; the CLI reports and exits non-zero
+    r = subprocess.run([exe, str(csv), "5", "3", "0.1", "5", str(out)], capture_output=True, text=True)
+    assert r.returncode != 0 and "k = 5" in r.stderr
