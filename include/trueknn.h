@@ -63,6 +63,8 @@ enum {
   TKNN_OPT_RADIUS_QUANTILE = 7 /* start-radius estimator: per-mille quantile of the sampled k-th
                                   neighbour distance (default 990)                                */
   ,TKNN_OPT_KEEP_SCRATCH = 8   /* 1 (default): keep the build scratch buffers for the next tknn_build    */
+  ,TKNN_OPT_APPROX_FILTER = 10 /* 1: conservative 3-FMA pre-filter before the exact distance test
+                                  (audited, -1 % time); 0 (default): exact test on every pair */
   ,TKNN_OPT_SPARSE_DIVISOR = 9 /* rounds >= 2 with fewer than n/divisor active queries run the
                                   thread-per-query kernel (default 8; 0 = never)                  */
 };
@@ -104,6 +106,7 @@ typedef struct tknn_stats {
   uint64_t warp_node_visits;/* node records actually loaded (once per warp)                   */
   uint64_t warp_leaf_visits;/* leaves actually loaded (once per warp)                         */
   uint64_t warp_point_loads;/* float4 points actually loaded (once per warp)                  */
+  uint64_t filter_violations;/* counting build: pairs the pre-filter rejected but the exact test accepts; must be 0 */
   uint64_t h2d_bytes, d2h_bytes; /* staging traffic of the last build / search */
 } tknn_stats;
 

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtrueknn.so")
+LIB_PATH = os.environ.get("TKNN_LIB_PATH") or os.path.join(_HERE, "lib", "libtrueknn.so")  # override: kernel A/B experiments
 
 TKNN_MAX_ROUNDS = 48
 TKNN_MAX_K = 512
@@ -19,7 +19,7 @@ OK, EINVAL, ENOMEM, ECUDA, ENCCL, ESTATE = 0, 1, 2, 3, 4, 5
 ERROR_NAMES = {0: "TKNN_OK", 1: "TKNN_EINVAL", 2: "TKNN_ENOMEM", 3: "TKNN_ECUDA", 4: "TKNN_ENCCL", 5: "TKNN_ESTATE"}
 
 (OPT_LEAF_SIZE, OPT_COUNTERS, OPT_LEAF_POLICY, OPT_SAMPLE_GROUPS, OPT_BLOCKS_PER_SM, OPT_SQUARED_DIST, OPT_RADIUS_QUANTILE,
- OPT_KEEP_SCRATCH, OPT_SPARSE_DIVISOR) = (1, 2, 3, 4, 5, 6, 7, 8, 9)
+ OPT_KEEP_SCRATCH, OPT_SPARSE_DIVISOR, OPT_APPROX_FILTER) = (1, 2, 3, 4, 5, 6, 7, 8, 9, 10)
 
 
 class Stats(C.Structure):
@@ -54,6 +54,7 @@ class Stats(C.Structure):
         ("warp_node_visits", C.c_uint64),
         ("warp_leaf_visits", C.c_uint64),
         ("warp_point_loads", C.c_uint64),
+        ("filter_violations", C.c_uint64),
         ("h2d_bytes", C.c_uint64),
         ("d2h_bytes", C.c_uint64),
     ]

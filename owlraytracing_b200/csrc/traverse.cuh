@@ -47,7 +47,8 @@ struct Params {
   uint32_t* unresolved;      // one ballot word per group
   uint32_t* group_counter;   // persistent-grid work counter
   unsigned long long* counters;  // [0] node visits x active lanes, [1] point tests x active lanes, [2] inserts,
-                                 // [3] warp node loads, [4] warp leaf loads, [5] warp point loads
+                                 // [3] warp node loads, [4] warp leaf loads, [5] warp point loads,
+                                 // [6] pre-filter violations (must stay 0)
 };
 
 // ---- bounded max-heap of u64 keys in shared memory, slot s of lane l at H[s * 32 + l] ----------
@@ -90,16 +91,16 @@ __device__ __forceinline__ void list_insert(uint64_t* L, int& cnt, int k, uint64
   uint64_t* p = L + (cnt < k ? cnt + 1 : k) * 32;  // the slot being filled
   if (cnt < k) ++cnt;
   for (;;) {
-    const uint64_t a = *(p - 32);
+    // four independent loads in flight: one shared-memory latency per four steps.  Slots below the
+    // sentinel (at most three) are never used: the walk stops at the sentinel; they lie inside this
+    // warp's own staging area, so the reads are in bounds.
+    const uint64_t a = *(p - 32), b = *(p - 64), c = *(p - 96), d = *(p - 128);
     if (a <= key) { *p = key; return; }
     *p = a;
-    const uint64_t b = *(p - 64);
     if (b <= key) { *(p - 32) = key; return; }
     *(p - 32) = b;
-    const uint64_t c = *(p - 96);
     if (c <= key) { *(p - 64) = key; return; }
     *(p - 64) = c;
-    const uint64_t d = *(p - 128);
     if (d <= key) { *(p - 96) = key; return; }
     *(p - 96) = d;
     p -= 128;
@@ -143,10 +144,32 @@ __device__ __forceinline__ void kl_emit(uint64_t* H, int cnt, int k, bool heap, 
 }
 
 __host__ __device__ inline size_t smem_per_warp(int k) {
-  return (size_t)(k + 1) * 32 * sizeof(uint64_t) + MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int);
+  return (size_t)(k + 1) * 32 * sizeof(uint64_t) + 2 * MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int);
 }
 
-template <int MODE, bool COUNT>
+// ---- conservative pre-filter -------------------------------------------------------------------
+// The exact test costs 6 FP instructions per (query, point).  With coordinates taken relative to a
+// group-local origin c (lane 0's query), qr = q - c and pr = p - c are small, and
+//     t = fma(-2qr.x, pr.x, fma(-2qr.y, pr.y, fma(-2qr.z, pr.z, |pr|^2)))  ~  |q - p|^2 - |qr|^2
+// costs 3.  A point passes the pre-filter iff t <= tau with tau = bound - |qr|^2 + margin; survivors
+// are re-tested with the exact fmaf chain in the insert loop, so false positives cost time, never
+// correctness.  No false negatives: writing u = 2^-23 and R = |qr| + |pr|, the roundings of qr, pr
+// (<= u R per vector), of |pr|^2 and |qr|^2 (3 ops each) and of the three fmas (each <= u R^2) put the
+// computed t + |qr|^2 within 19 u R^2 of the exact chain's d2 (whose own relative error is <= 6u), and
+// any point with d2 <= bound has |pr| <= |qr| + 1.01 sqrt(bound), i.e. R^2 <= 8|qr|^2 + 2.1 bound.  So
+// margin = 19u (8|qr|^2 + 2.1 bound) ~ 1.8e-5 |qr|^2 + 4.8e-6 bound suffices; the kernel uses
+// 1e-4 |qr|^2 + 2e-5 bound (5x slack).  Non-finite or huge operands fall back to tau = +inf (all pass).
+// The counting build (TKNN_OPT_COUNTERS) also evaluates the exact test for every pair and counts
+// violations (tknn_stats.filter_violations, asserted zero by the tests).
+// Measured on cfg2: 8.45 ms vs 8.54 ms for the exact filter (-1 %): the 3 FFMA per pair saturate the FMA
+// pipe (one warp instruction per two cycles) where the exact form splits 3 FADD (ALU pipe) / 3 FMUL+FFMA.
+// It is therefore OFF by default (TKNN_OPT_APPROX_FILTER) — kept as a measured, audited option.
+__device__ __forceinline__ float prefilter_tau(float bound, float qq) {
+  const float tau = __fadd_rn(__fsub_rn(bound, qq), __fmaf_rn(1e-4f, qq, __fmul_rn(2e-5f, bound)));
+  return (qq < 1e30f && bound < 1e30f) ? tau : INFINITY;
+}
+
+template <int MODE, bool COUNT, bool APPROX>
 __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -156,8 +179,11 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
   float4* stage = reinterpret_cast<float4*>(wbase);
   int* stack = reinterpret_cast<int*>(wbase + MAX_LEAF * sizeof(float4));
   uint64_t* H = reinterpret_cast<uint64_t*>(wbase + MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int)) + lane;
+  // second staging array (relative coordinates + squared norm) for the pre-filter, behind the k-list
+  float4* stage2 = reinterpret_cast<float4*>(wbase + MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int) +
+                                             (size_t)(k + 1) * 32 * sizeof(uint64_t));
 
-  unsigned long long c_nodes = 0, c_tests = 0, c_ins = 0, c_wnodes = 0, c_wleaves = 0, c_wpts = 0;
+  unsigned long long c_nodes = 0, c_tests = 0, c_ins = 0, c_wnodes = 0, c_wleaves = 0, c_wpts = 0, c_viol = 0;
 
   for (;;) {
     uint32_t group = 0;
@@ -179,6 +205,14 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
     float bound = valid ? r2 : -1.0f;  // d2 >= 0 > -1: an idle lane never wants anything
     int cnt = 0;
     if (MODE == MODE_KNN) H[0] = 0;    // sentinel of this lane's k-list
+    // group-local origin and this lane's pre-filter constants
+    float ax, ay, az, qq;
+    {
+      const float cx = __shfl_sync(FULL_MASK, q.x, 0), cy = __shfl_sync(FULL_MASK, q.y, 0), cz = __shfl_sync(FULL_MASK, q.z, 0);
+      const float qrx = __fsub_rn(q.x, cx), qry = __fsub_rn(q.y, cy), qrz = __fsub_rn(q.z, cz);
+      ax = -2.0f * qrx; ay = -2.0f * qry; az = -2.0f * qrz;
+      qq = __fmaf_rn(qrz, qrz, __fmaf_rn(qry, qry, __fmul_rn(qrx, qrx)));
+    }
 
     int sp = 0;
     int node = 0;
@@ -205,7 +239,18 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
           const float dc = second ? d1 : d0;
           if (!__any_sync(FULL_MASK, dc <= bound)) continue;
           const int start = second ? ref1 : ref0;
-          if (lane < lcount) stage[lane] = __ldg(&P.pts[(uint64_t)(uint32_t)start + lane]);
+          float cx = 0.f, cy = 0.f, cz = 0.f;
+          if (APPROX && MODE == MODE_KNN) {  // the group origin = lane 0's query (re-broadcast: saves 3 registers)
+            cx = __shfl_sync(FULL_MASK, q.x, 0); cy = __shfl_sync(FULL_MASK, q.y, 0); cz = __shfl_sync(FULL_MASK, q.z, 0);
+          }
+          if (lane < lcount) {
+            const float4 pl = __ldg(&P.pts[(uint64_t)(uint32_t)start + lane]);
+            stage[lane] = pl;
+            if (APPROX && MODE == MODE_KNN) {
+              const float rx = __fsub_rn(pl.x, cx), ry = __fsub_rn(pl.y, cy), rz = __fsub_rn(pl.z, cz);
+              stage2[lane] = make_float4(rx, ry, rz, __fmaf_rn(rz, rz, __fmaf_rn(ry, ry, __fmul_rn(rx, rx))));
+            }
+          }
           __syncwarp();
           if (COUNT) { c_tests += valid ? lcount : 0; c_wleaves += 1; c_wpts += lcount; }
           if (MODE == MODE_RANGE_COUNT) {
@@ -218,20 +263,46 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
             // filter: full chunks of 8 with compile-time bit positions, then the remainder one by one
             uint32_t mask = 0;
             int j0 = 0;
-            for (; j0 + 8 <= lcount; j0 += 8) {
-              uint32_t m8 = 0;
+            if (APPROX) {
+              const float tau = valid ? prefilter_tau(bound, qq) : -INFINITY;
+              for (; j0 + 8 <= lcount; j0 += 8) {
+                uint32_t m8 = 0;
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                const float4 p = stage[j0 + jj];
-                const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
-                if (d <= bound) m8 |= (1u << jj);
+                for (int jj = 0; jj < 8; ++jj) {
+                  const float4 p = stage2[j0 + jj];
+                  const float t = __fmaf_rn(ax, p.x, __fmaf_rn(ay, p.y, __fmaf_rn(az, p.z, p.w)));
+                  if (t <= tau) m8 |= (1u << jj);
+                }
+                mask |= m8 << j0;
               }
-              mask |= m8 << j0;
-            }
-            for (; j0 < lcount; ++j0) {
-              const float4 p = stage[j0];
-              const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
-              if (d <= bound) mask |= (1u << j0);
+              for (; j0 < lcount; ++j0) {
+                const float4 p = stage2[j0];
+                const float t = __fmaf_rn(ax, p.x, __fmaf_rn(ay, p.y, __fmaf_rn(az, p.z, p.w)));
+                if (t <= tau) mask |= (1u << j0);
+              }
+              if (COUNT) {  // audit: an exactly-passing pair the pre-filter rejected would be a wrong result
+                for (int j = 0; j < lcount; ++j) {
+                  const float4 p = stage[j];
+                  const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+                  if (valid && d <= bound && !((mask >> j) & 1u)) c_viol += 1;
+                }
+              }
+            } else {
+              for (; j0 + 8 <= lcount; j0 += 8) {
+                uint32_t m8 = 0;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                  const float4 p = stage[j0 + jj];
+                  const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+                  if (d <= bound) m8 |= (1u << jj);
+                }
+                mask |= m8 << j0;
+              }
+              for (; j0 < lcount; ++j0) {
+                const float4 p = stage[j0];
+                const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+                if (d <= bound) mask |= (1u << j0);
+              }
             }
             // insert: only lanes with survivors do work; the bound tightens as they go
             while (__any_sync(FULL_MASK, mask != 0u)) {
@@ -304,6 +375,7 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
     atomicAdd(&P.counters[0], c_nodes);
     atomicAdd(&P.counters[1], c_tests);
     atomicAdd(&P.counters[2], c_ins);
+    if (c_viol) atomicAdd(&P.counters[6], c_viol);
     if (lane == 0) {
       atomicAdd(&P.counters[3], c_wnodes);
       atomicAdd(&P.counters[4], c_wleaves);
@@ -321,14 +393,15 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
 // ------------------------------------------------------------------------------------------------
 constexpr int SPARSE_THREADS = 128;
 
-__host__ __device__ inline size_t sparse_smem(int k) { return (size_t)(k + 1) * SPARSE_THREADS * sizeof(uint64_t); }
+// + 3 slots of padding in front: list_insert prefetches up to three slots below the sentinel
+__host__ __device__ inline size_t sparse_smem(int k) { return ((size_t)(k + 1) * SPARSE_THREADS + 3 * 32) * sizeof(uint64_t); }
 
 template <bool COUNT>
 __global__ void __launch_bounds__(SPARSE_THREADS) traverse_sparse_kernel(const Params P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = P.k;
-  uint64_t* H = reinterpret_cast<uint64_t*>(smem) + (size_t)warp * (k + 1) * 32 + lane;
+  uint64_t* H = reinterpret_cast<uint64_t*>(smem) + 3 * 32 + (size_t)warp * (k + 1) * 32 + lane;
   H[0] = 0;  // sentinel
   const bool heap = k > LIST_MAX_K;
   int stack[STACK_DEPTH];

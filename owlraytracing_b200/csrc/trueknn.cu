@@ -53,6 +53,7 @@ struct tknn_ctx {
       b_parent_leaf, b_parent_node, b_arrive;
   int keep_scratch = 1;
   int sparse_divisor = 8;
+  int approx_filter = 0;
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> round_ev;
   tknn_stats stats;
@@ -121,7 +122,7 @@ inline unsigned blocks_for(uint64_t n, int threads) { return (unsigned)((n + thr
 
 // scalars layout (uint32 words unless noted)
 enum { SC_GROUP_COUNTER = 0, SC_TOTAL = 1, SC_ERROR = 2, SC_BOUNDS = 4 /* 7 words */, SC_SCENE = 12 /* 6 floats */,
-       SC_COUNTERS = 20 /* 6 x u64, 8-byte aligned */, SC_WORDS = 40 };
+       SC_COUNTERS = 20 /* 8 x u64, 8-byte aligned */, SC_WORDS = 44 };
 
 // exclusive scan of popc(words[0..nw)) into offsets, total into scalars[SC_TOTAL]
 int popc_scan(tknn_ctx* c, const uint32_t* words, uint64_t nw, uint32_t* offsets, int* launches) {
@@ -178,15 +179,12 @@ int launch_traverse(tknn_ctx* c, const trav::Params& P) {
   uint64_t grid = (uint64_t)c->sm_count * bps;
   const uint64_t need = ((uint64_t)P.n_groups + warps - 1) / warps;
   if (grid > need) grid = std::max<uint64_t>(1, need);
-  if (c->counters) {
-    auto kern = trav::traverse_kernel<MODE, true>;
-    TK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)grid, warps * 32, smem, c->stream>>>(P);
-  } else {
-    auto kern = trav::traverse_kernel<MODE, false>;
-    TK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)grid, warps * 32, smem, c->stream>>>(P);
-  }
+  void (*kern)(const trav::Params) = nullptr;
+  const bool approx = MODE == trav::MODE_KNN && c->approx_filter;
+  if (c->counters) kern = approx ? trav::traverse_kernel<MODE, true, true> : trav::traverse_kernel<MODE, true, false>;
+  else kern = approx ? trav::traverse_kernel<MODE, false, true> : trav::traverse_kernel<MODE, false, false>;
+  TK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)grid, warps * 32, smem, c->stream>>>(P);
   TK_CUDA(c, cudaGetLastError());
   return TKNN_OK;
 }
@@ -363,7 +361,7 @@ int read_error_flag(tknn_ctx* c) {
 
 int collect_counters(tknn_ctx* c) {
   if (!c->counters) return TKNN_OK;
-  unsigned long long h[6];
+  unsigned long long h[8];
   TK_CUDA(c, cudaMemcpyAsync(h, c->scalars.as<uint32_t>() + SC_COUNTERS, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   TK_CUDA(c, cudaStreamSynchronize(c->stream));
   c->stats.nodes_visited = h[0];
@@ -372,6 +370,7 @@ int collect_counters(tknn_ctx* c) {
   c->stats.warp_node_visits = h[3];
   c->stats.warp_leaf_visits = h[4];
   c->stats.warp_point_loads = h[5];
+  c->stats.filter_violations = h[6];
   return TKNN_OK;
 }
 
@@ -395,7 +394,7 @@ void reset_search_stats(tknn_ctx* c) {
   std::memset(s.round_queries, 0, sizeof(s.round_queries));
   s.kernel_launches = 0;
   s.nodes_visited = s.points_tested = s.heap_inserts = 0;
-  s.warp_node_visits = s.warp_leaf_visits = s.warp_point_loads = 0;
+  s.warp_node_visits = s.warp_leaf_visits = s.warp_point_loads = s.filter_violations = 0;
   s.d2h_bytes = 0;
 }
 
@@ -430,7 +429,7 @@ int search_range(tknn_ctx* c, int k, float start_radius, uint64_t q_begin, uint6
   }
 
   TK_CUDA(c, cudaMemsetAsync(sc + SC_ERROR, 0, sizeof(uint32_t), c->stream));
-  TK_CUDA(c, cudaMemsetAsync(sc + SC_COUNTERS, 0, 6 * sizeof(unsigned long long), c->stream));
+  TK_CUDA(c, cudaMemsetAsync(sc + SC_COUNTERS, 0, 8 * sizeof(unsigned long long), c->stream));
   TK_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
   int launches = 0;
   float r0 = start_radius;
@@ -561,6 +560,7 @@ int tknn_set_option(tknn_ctx* c, int key, int64_t value) {
       return TKNN_OK;
     case TKNN_OPT_SQUARED_DIST: c->squared = value ? 1 : 0; return TKNN_OK;
     case TKNN_OPT_KEEP_SCRATCH: c->keep_scratch = value ? 1 : 0; return TKNN_OK;
+    case TKNN_OPT_APPROX_FILTER: c->approx_filter = value ? 1 : 0; return TKNN_OK;
     case TKNN_OPT_SPARSE_DIVISOR:
       if (value < 0 || value > 1000000) return fail(c, TKNN_EINVAL, "sparse divisor outside [0, 1e6]");
       c->sparse_divisor = (int)value;
@@ -862,7 +862,7 @@ int tknn_query(tknn_ctx* c, const float* queries, uint64_t nq, int dim, int stri
   if (!dist_dev) { TK_B(ensure(c, c->stage_dist, out_elems * sizeof(float))); d_dist = c->stage_dist.as<float>(); }
 
   TK_BC(cudaMemsetAsync(sc + SC_ERROR, 0, sizeof(uint32_t), st));
-  TK_BC(cudaMemsetAsync(sc + SC_COUNTERS, 0, 6 * sizeof(unsigned long long), st));
+  TK_BC(cudaMemsetAsync(sc + SC_COUNTERS, 0, 8 * sizeof(unsigned long long), st));
   float r0 = start_radius;
   // a query set can hold fewer than k reachable neighbours only through self exclusion / radius caps
   const bool may_underfill = (uint64_t)k > c->n - (self_ids ? 1 : 0);
@@ -931,7 +931,7 @@ int tknn_range_count(tknn_ctx* c, float radius, uint32_t* count_out) {
   P.group_counter = sc + SC_GROUP_COUNTER;
   P.counters = c->counters ? reinterpret_cast<unsigned long long*>(sc + SC_COUNTERS) : nullptr;
   TK_CUDA(c, cudaMemsetAsync(sc + SC_ERROR, 0, sizeof(uint32_t), c->stream));
-  TK_CUDA(c, cudaMemsetAsync(sc + SC_COUNTERS, 0, 6 * sizeof(unsigned long long), c->stream));
+  TK_CUDA(c, cudaMemsetAsync(sc + SC_COUNTERS, 0, 8 * sizeof(unsigned long long), c->stream));
   TK_CUDA(c, cudaMemsetAsync(sc + SC_GROUP_COUNTER, 0, sizeof(uint32_t), c->stream));
   TK_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
   TK_TRY(launch_traverse<trav::MODE_RANGE_COUNT>(c, P));

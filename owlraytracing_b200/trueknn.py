@@ -96,6 +96,7 @@ class TrueKNN:
         "sample_groups": _lib.OPT_SAMPLE_GROUPS, "blocks_per_sm": _lib.OPT_BLOCKS_PER_SM,
         "squared_dist": _lib.OPT_SQUARED_DIST, "radius_quantile": _lib.OPT_RADIUS_QUANTILE,
         "keep_scratch": _lib.OPT_KEEP_SCRATCH, "sparse_divisor": _lib.OPT_SPARSE_DIVISOR,
+        "approx_filter": _lib.OPT_APPROX_FILTER,
     }
 
     def set_option(self, name: str, value: int):

@@ -330,3 +330,51 @@ def test_cpp_cli_end_to_end(oracle, tmp_path):
     # k > n - 1: the reference loops forever; the CLI reports and exits non-zero
     r = subprocess.run([exe, str(csv), "5", "3", "0.1", "5", str(out)], capture_output=True, text=True)
     assert r.returncode != 0 and "k = 5" in r.stderr
+
+
+@pytest.mark.parametrize("cloud", ["uniform", "offset_1e4", "offset_1e6_tiny_spread", "lattice", "lidar", "two_scales", "huge"])
+def test_prefilter_never_rejects_a_true_candidate(knn, oracle, cloud):
+    """The 3-FMA pre-filter is conservative: the counting build audits every (query, point)
+    pair against the exact test; results with the filter on and off are identical and equal the oracle."""
+    rng = np.random.default_rng(17)
+    if cloud == "uniform":
+        x = datasets.uniform(60_000, seed=2)
+    elif cloud == "offset_1e4":
+        x = datasets.uniform(40_000, seed=3) + np.float32(1e4)
+    elif cloud == "offset_1e6_tiny_spread":
+        x = (rng.random((30_000, 3)) * 8).astype(np.float32) + np.float32(1e6)   # spacing ~ a few ulps: massive ties
+    elif cloud == "lattice":
+        x = datasets.lattice(30) * np.float32(0.1) + np.float32(3.0)
+    elif cloud == "lidar":
+        x = datasets.lidar_like(80_000, seed=11)
+    elif cloud == "two_scales":
+        x = np.concatenate([datasets.uniform(20_000, seed=5) * np.float32(1e-3), datasets.uniform(20_000, seed=6) * np.float32(1e3)])
+    else:
+        x = (datasets.uniform(20_000, seed=7) - np.float32(0.5)) * np.float32(1e18)  # squares overflow fp32
+    x = np.ascontiguousarray(x, np.float32)
+    k = 12
+    ref = oracle.knn_kdtree(x, k)
+    knn.set_option("counters", 1)
+    knn.set_option("approx_filter", 1)
+    idx, dist = knn.build(x).search(k)
+    st = knn.stats()
+    assert st["filter_violations"] == 0
+    assert_knn_equal(idx, dist, *ref, f"{cloud} (pre-filter on)")
+    knn.set_option("approx_filter", 0)
+    idx0, dist0 = knn.search(k)
+    assert (idx0 == idx).all() and (dist0 == dist).all()
+    for r0 in (float("inf"), 1e-3):
+        knn.set_option("approx_filter", 1)
+        i2, d2 = knn.search(k, start_radius=r0)
+        assert knn.stats()["filter_violations"] == 0
+        assert (i2 == idx).all() and (d2 == dist).all()
+
+
+@pytest.mark.parametrize("k", [24, 25, 100, 256, 512])
+def test_large_k_heap_path(knn, oracle, k):
+    """k > 24 switches the per-lane k-list from the ascending list to the binary heap; k = 512 is TKNN_MAX_K."""
+    x = datasets.lidar_like(6000, seed=13)
+    ref = oracle.knn_kdtree(x, k)
+    for r0 in (0.0, 0.05):
+        idx, dist = knn.build(x).search(k, start_radius=r0)
+        assert_knn_equal(idx, dist, *ref, f"k={k} r0={r0}")
