@@ -314,10 +314,19 @@ def run_gpu(args):
         dst_h = torch.empty((cap, k), dtype=torch.float32, pin_memory=True)
         xh_np, out_np = xh.numpy(), (qid_h.numpy(), idx_h.numpy(), dst_h.numpy())
 
+        full_np = (idx_h.numpy()[:n_points], dst_h.numpy()[:n_points]) if world == 1 else None
+
         def e2e_step():
             t.build(xh_np)                                     # H2D of the points + LBVH build
+            if world == 1 and not args.e2e_shard_api:
+                # the reference-facing call: rows in file order (tknn_search), search + D2H
+                return t.search(k, args.start_radius, out=full_np)
             return t.search_shard(k, rank, world, start_radius=args.start_radius, out=out_np)  # search + D2H
 
+        if args.output_chunks > 0:
+            t.set_option("output_chunks", args.output_chunks)
+        if args.file_order_chunks > 0:
+            t.set_option("file_order_chunks", args.file_order_chunks)
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         e2e_step()
         barrier()
@@ -336,7 +345,9 @@ def run_gpu(args):
         e_ms = float(tm[0].item()) / e2e_steps
         e2e = {"value": total_queries / (e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": int(n_points * 12),
                "d2h_bytes_per_step": int(es["d2h_bytes"]), "ms_per_step": e_ms, "wall_ms_per_step": float(tm[1].item()) / e2e_steps,
-               "steps": e2e_steps, "includes": "H2D points (pinned) + LBVH build + search (all rounds) + D2H results (pinned)"}
+               "steps": e2e_steps, "includes": "H2D points (pinned) + LBVH build + search (all rounds) + D2H results (pinned)",
+               "api": "tknn_build + tknn_search (rows in file order)" if (world == 1 and not args.e2e_shard_api)
+               else "tknn_build + tknn_search_shard (compact Morton-order rows + query ids)"}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None
@@ -383,6 +394,9 @@ def main():
     ap.add_argument("--start-radius", type=float, default=0.0, help="<= 0: auto")
     ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="queries per CPU step")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--output-chunks", type=int, default=0, help="e2e: Morton slices whose D2H overlaps the search (0 = library default)")
+    ap.add_argument("--file-order-chunks", type=int, default=0, help="e2e through tknn_search: slices by original index (0 = default)")
+    ap.add_argument("--e2e-shard-api", action="store_true", help="N=1 e2e through tknn_search_shard (compact Morton rows) instead of tknn_search")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

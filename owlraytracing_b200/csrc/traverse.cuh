@@ -498,6 +498,20 @@ __global__ void __launch_bounds__(SPARSE_THREADS) traverse_sparse_kernel(const P
   }
 }
 
+// Ballot words of "the point at sorted position p has an original index in [lo, hi)": the first step of
+// cutting the query list into FILE-order slices whose output rows are contiguous (pipelined host output).
+__global__ void __launch_bounds__(256) index_range_flag_kernel(const float4* __restrict__ pts, uint64_t n, uint32_t lo,
+                                                               uint32_t hi, uint32_t* __restrict__ words) {
+  const uint64_t p = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  bool in = false;
+  if (p < n) {
+    const uint32_t id = __float_as_uint(__ldg(&pts[p]).w);
+    in = id >= lo && id < hi;
+  }
+  const uint32_t w = __ballot_sync(FULL_MASK, in);
+  if ((threadIdx.x & 31) == 0 && p < n) words[p >> 5] = w;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Round compaction: unresolved ballot words -> the next round's queue, order preserved (so the
 // next round's groups are still Morton-coherent).  offsets[] = exclusive scan of popc(words).

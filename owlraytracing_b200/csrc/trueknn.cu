@@ -36,7 +36,7 @@ struct tknn_ctx {
   int device = 0;
   int sm_count = 148;
   size_t l2_bytes = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
   std::string err;
   // options
   int leaf_size = 32, counters = 0, leaf_policy = 0, sample_groups = 128, blocks_per_sm = 0, squared = 0,
@@ -54,6 +54,10 @@ struct tknn_ctx {
   int keep_scratch = 1;
   int sparse_divisor = 8;
   int approx_filter = 0;
+  int output_chunks = 4;  // host-output pipelining: slices whose D2H overlaps the next slice's search (1 = off)
+  int file_order_chunks = 4;  // same for tknn_search (file-order rows): slices by original index (1 = off)
+  DevBuf chunk_queue;
+  std::vector<cudaEvent_t> chunk_ev;
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> round_ev;
   tknn_stats stats;
@@ -451,20 +455,111 @@ int search_range(tknn_ctx* c, int k, float start_radius, uint64_t q_begin, uint6
   job.idx_out = d_idx;
   job.dist_out = d_dist;
   job.qid_out = d_qid;
-  TK_TRY(run_rounds(c, job, &launches));
-  TK_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
 
-  if (!idx_dev) {
-    TK_CUDA(c, cudaMemcpyAsync(idx_out, d_idx, out_elems * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    c->stats.d2h_bytes += out_elems * sizeof(int32_t);
-  }
-  if (!dist_dev) {
-    TK_CUDA(c, cudaMemcpyAsync(dist_out, d_dist, out_elems * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    c->stats.d2h_bytes += out_elems * sizeof(float);
-  }
-  if (qid_out && !qid_dev) {
-    TK_CUDA(c, cudaMemcpyAsync(qid_out, d_qid, rows * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    c->stats.d2h_bytes += rows * sizeof(int32_t);
+  // Compact rows (row_mode 1) are in Morton order, so a contiguous slice of the queries yields a
+  // contiguous, FINAL slice of the output: with host outputs the shard is searched in chunks and each
+  // chunk's device->host copy (copy stream) overlaps the search of the next one (compute stream).
+  const uint64_t groups = (nq + 31) / 32;
+  const bool host_out = !idx_dev || !dist_dev || (qid_out && !qid_dev);
+  const int chunks = (row_mode == 1 && host_out && c->output_chunks > 1 && nq >= (1u << 18))
+                         ? (int)std::min<uint64_t>((uint64_t)c->output_chunks, groups) : 1;
+  if (chunks > 1) {
+    while ((int)c->chunk_ev.size() < chunks) {
+      cudaEvent_t e;
+      TK_CUDA(c, cudaEventCreate(&e));
+      c->chunk_ev.push_back(e);
+    }
+    for (int ci = 0; ci < chunks; ++ci) {
+      const uint64_t g0 = groups * (uint64_t)ci / chunks, g1 = groups * (uint64_t)(ci + 1) / chunks;
+      const uint64_t r_lo = g0 * 32, r_hi = std::min<uint64_t>(nq, g1 * 32);  // rows of this chunk
+      if (r_hi <= r_lo) continue;
+      Job cj = job;
+      cj.q_begin = q_begin + r_lo;
+      cj.n_queries = r_hi - r_lo;
+      cj.idx_out = d_idx + r_lo * (uint64_t)k;
+      cj.dist_out = d_dist + r_lo * (uint64_t)k;
+      cj.qid_out = d_qid ? d_qid + r_lo : nullptr;
+      cj.record_stats = (ci == 0);  // per-round figures describe the first chunk
+      TK_TRY(run_rounds(c, cj, &launches));
+      TK_CUDA(c, cudaEventRecord(c->chunk_ev[ci], c->stream));
+      TK_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->chunk_ev[ci], 0));
+      const size_t e0 = (size_t)r_lo * k, ne = (size_t)(r_hi - r_lo) * k;
+      if (!idx_dev) {
+        TK_CUDA(c, cudaMemcpyAsync(idx_out + e0, d_idx + e0, ne * sizeof(int32_t), cudaMemcpyDeviceToHost, c->copy_stream));
+        c->stats.d2h_bytes += ne * sizeof(int32_t);
+      }
+      if (!dist_dev) {
+        TK_CUDA(c, cudaMemcpyAsync(dist_out + e0, d_dist + e0, ne * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+        c->stats.d2h_bytes += ne * sizeof(float);
+      }
+      if (qid_out && !qid_dev) {
+        TK_CUDA(c, cudaMemcpyAsync(qid_out + r_lo, d_qid + r_lo, (r_hi - r_lo) * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                   c->copy_stream));
+        c->stats.d2h_bytes += (r_hi - r_lo) * sizeof(int32_t);
+      }
+    }
+    TK_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    // the caller's stream must not run ahead of the copies
+    TK_CUDA(c, cudaEventRecord(c->chunk_ev[0], c->copy_stream));
+    TK_CUDA(c, cudaStreamWaitEvent(c->stream, c->chunk_ev[0], 0));
+  } else if (row_mode == 0 && host_out && c->file_order_chunks > 1 && nq == c->n && nq >= (1u << 18)) {
+    // File-order rows: slice the queries by ORIGINAL index so that each slice's rows are one contiguous,
+    // final block of the output.  A slice is every C-th point of the cloud in Morton order, so its groups
+    // are C times less dense in space (costlier per query) — the price of overlapping the result copy.
+    const int fc = c->file_order_chunks;
+    while ((int)c->chunk_ev.size() < fc) {
+      cudaEvent_t e;
+      TK_CUDA(c, cudaEventCreate(&e));
+      c->chunk_ev.push_back(e);
+    }
+    TK_TRY(ensure(c, c->chunk_queue, (size_t)nq * sizeof(uint32_t)));
+    TK_TRY(ensure(c, c->unresolved, sizeof(uint32_t) * (size_t)(groups + 1)));
+    TK_TRY(ensure(c, c->offsets, sizeof(uint32_t) * (size_t)(groups + 1)));
+    for (int ci = 0; ci < fc; ++ci) {
+      const uint64_t lo = nq * (uint64_t)ci / fc, hi = nq * (uint64_t)(ci + 1) / fc;
+      if (hi <= lo) continue;
+      uint32_t* cq = c->chunk_queue.as<uint32_t>() + lo;
+      trav::index_range_flag_kernel<<<blocks_for(nq, 256), 256, 0, c->stream>>>(c->pts.as<float4>(), nq, (uint32_t)lo,
+                                                                               (uint32_t)hi, c->unresolved.as<uint32_t>());
+      TK_TRY(popc_scan(c, c->unresolved.as<uint32_t>(), groups, c->offsets.as<uint32_t>(), &launches));
+      trav::compact_queue_kernel<<<blocks_for(groups * 32, 256), 256, 0, c->stream>>>(
+          c->unresolved.as<uint32_t>(), c->offsets.as<uint32_t>(), (uint32_t)groups, nullptr, 0, cq);
+      launches += 2;
+      Job cj = job;
+      cj.first_queue = cq;
+      cj.n_queries = hi - lo;
+      cj.record_stats = (ci == 0);
+      TK_TRY(run_rounds(c, cj, &launches));
+      TK_CUDA(c, cudaEventRecord(c->chunk_ev[ci], c->stream));
+      TK_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->chunk_ev[ci], 0));
+      const size_t e0 = (size_t)lo * k, ne = (size_t)(hi - lo) * k;
+      if (!idx_dev) {
+        TK_CUDA(c, cudaMemcpyAsync(idx_out + e0, d_idx + e0, ne * sizeof(int32_t), cudaMemcpyDeviceToHost, c->copy_stream));
+        c->stats.d2h_bytes += ne * sizeof(int32_t);
+      }
+      if (!dist_dev) {
+        TK_CUDA(c, cudaMemcpyAsync(dist_out + e0, d_dist + e0, ne * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+        c->stats.d2h_bytes += ne * sizeof(float);
+      }
+    }
+    TK_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    TK_CUDA(c, cudaEventRecord(c->chunk_ev[0], c->copy_stream));
+    TK_CUDA(c, cudaStreamWaitEvent(c->stream, c->chunk_ev[0], 0));
+  } else {
+    TK_TRY(run_rounds(c, job, &launches));
+    TK_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    if (!idx_dev) {
+      TK_CUDA(c, cudaMemcpyAsync(idx_out, d_idx, out_elems * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+      c->stats.d2h_bytes += out_elems * sizeof(int32_t);
+    }
+    if (!dist_dev) {
+      TK_CUDA(c, cudaMemcpyAsync(dist_out, d_dist, out_elems * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+      c->stats.d2h_bytes += out_elems * sizeof(float);
+    }
+    if (qid_out && !qid_dev) {
+      TK_CUDA(c, cudaMemcpyAsync(qid_out, d_qid, rows * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+      c->stats.d2h_bytes += rows * sizeof(int32_t);
+    }
   }
   TK_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
   TK_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -508,6 +603,7 @@ int tknn_create(int device, tknn_ctx** out) {
   c->l2_bytes = (size_t)prop.l2CacheSize;
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return TKNN_ECUDA; }
   c->stream = c->own_stream;
+  if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return TKNN_ECUDA; }
   for (auto& ev : c->ev)
     if (cudaEventCreate(&ev) != cudaSuccess) { delete c; return TKNN_ECUDA; }
   if (cudaMalloc(&c->scalars.p, SC_WORDS * sizeof(uint32_t)) != cudaSuccess) { delete c; return TKNN_ENOMEM; }
@@ -521,12 +617,14 @@ int tknn_destroy(tknn_ctx* c) {
   ScopedDevice sd(c->device);
   cudaStreamSynchronize(c->stream);
   for (DevBuf* b : {&c->pts, &c->nodes, &c->leaf_start, &c->queue_a, &c->queue_b, &c->unresolved, &c->offsets,
-                    &c->block_sums, &c->scalars, &c->stage_idx, &c->stage_dist, &c->sample, &c->b_in, &c->b_keys_a,
+                    &c->block_sums, &c->scalars, &c->stage_idx, &c->stage_dist, &c->sample, &c->chunk_queue, &c->b_in, &c->b_keys_a,
                     &c->b_keys_b, &c->b_vals_a, &c->b_vals_b, &c->b_sort_tmp, &c->b_delta, &c->b_ballots, &c->b_leaf_key,
                     &c->b_child_info, &c->b_parent_leaf, &c->b_parent_node, &c->b_arrive})
     release(*b);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->round_ev) cudaEventDestroy(ev);
+  for (auto& ev : c->chunk_ev) cudaEventDestroy(ev);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return TKNN_OK;
@@ -561,6 +659,14 @@ int tknn_set_option(tknn_ctx* c, int key, int64_t value) {
     case TKNN_OPT_SQUARED_DIST: c->squared = value ? 1 : 0; return TKNN_OK;
     case TKNN_OPT_KEEP_SCRATCH: c->keep_scratch = value ? 1 : 0; return TKNN_OK;
     case TKNN_OPT_APPROX_FILTER: c->approx_filter = value ? 1 : 0; return TKNN_OK;
+    case TKNN_OPT_FILE_ORDER_CHUNKS:
+      if (value < 1 || value > 64) return fail(c, TKNN_EINVAL, "file-order chunks outside [1, 64]");
+      c->file_order_chunks = (int)value;
+      return TKNN_OK;
+    case TKNN_OPT_OUTPUT_CHUNKS:
+      if (value < 1 || value > 64) return fail(c, TKNN_EINVAL, "output chunks outside [1, 64]");
+      c->output_chunks = (int)value;
+      return TKNN_OK;
     case TKNN_OPT_SPARSE_DIVISOR:
       if (value < 0 || value > 1000000) return fail(c, TKNN_EINVAL, "sparse divisor outside [0, 1e6]");
       c->sparse_divisor = (int)value;

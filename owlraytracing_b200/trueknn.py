@@ -96,7 +96,8 @@ class TrueKNN:
         "sample_groups": _lib.OPT_SAMPLE_GROUPS, "blocks_per_sm": _lib.OPT_BLOCKS_PER_SM,
         "squared_dist": _lib.OPT_SQUARED_DIST, "radius_quantile": _lib.OPT_RADIUS_QUANTILE,
         "keep_scratch": _lib.OPT_KEEP_SCRATCH, "sparse_divisor": _lib.OPT_SPARSE_DIVISOR,
-        "approx_filter": _lib.OPT_APPROX_FILTER,
+        "approx_filter": _lib.OPT_APPROX_FILTER, "output_chunks": _lib.OPT_OUTPUT_CHUNKS,
+        "file_order_chunks": _lib.OPT_FILE_ORDER_CHUNKS,
     }
 
     def set_option(self, name: str, value: int):

@@ -378,3 +378,37 @@ def test_large_k_heap_path(knn, oracle, k):
     for r0 in (0.0, 0.05):
         idx, dist = knn.build(x).search(k, start_radius=r0)
         assert_knn_equal(idx, dist, *ref, f"k={k} r0={r0}")
+
+
+def test_pipelined_host_output_of_a_shard(knn, oracle):
+    """tknn_search_shard with HOST outputs searches the shard in Morton slices and overlaps each slice's
+    device->host copy with the next slice's search; results equal the single-pass device-output path."""
+    import torch
+
+    x = datasets.uniform(700_001, seed=21)
+    ref = oracle.knn_kdtree(x, 10)
+    knn.build(x)                                   # numpy => host outputs => pipelined (n >= 2^18)
+    qid, idx, dist = knn.search_shard(10, 0, 1)
+    assert np.array_equal(np.sort(qid), np.arange(x.shape[0]))
+    assert_knn_equal(idx, dist, ref[0][qid], ref[1][qid], "pipelined host output")
+    for chunks in (1, 3, 64):
+        knn.set_option("output_chunks", chunks)
+        q2, i2, d2 = knn.search_shard(10, 1, 2)
+        assert_knn_equal(i2, d2, ref[0][q2], ref[1][q2], f"chunks={chunks}")
+    knn.build(torch.from_numpy(x).cuda())          # device outputs: one pass
+    q3, i3, d3 = knn.search_shard(10, 0, 1)
+    assert np.array_equal(q3.cpu().numpy(), qid) and np.array_equal(i3.cpu().numpy(), idx)
+
+
+def test_pipelined_host_output_in_file_order(knn, oracle):
+    """tknn_search with HOST outputs slices the queries by original index (contiguous, final output rows per
+    slice) and overlaps each slice's copy with the next slice's search; any slice count gives the exact answer."""
+    x = datasets.lidar_like(400_000, seed=23)
+    ref = oracle.knn_kdtree(x, 8)
+    knn.build(x)
+    for chunks in (4, 1, 3, 64):
+        knn.set_option("file_order_chunks", chunks)
+        idx, dist = knn.search(8)
+        assert_knn_equal(idx, dist, *ref, f"file-order chunks={chunks}")
+    idx, dist = knn.search(8, start_radius=0.02)
+    assert_knn_equal(idx, dist, *ref, "file-order chunks, fixed radius")
