@@ -183,11 +183,15 @@ __global__ void __launch_bounds__(THREADS)
 // temp layout (uint32 words): hist[PASSES*RADIX] | counters[PASSES] (+pad to 16) | status[tiles*RADIX]
 inline size_t temp_words(uint64_t n) { return (size_t)PASSES * RADIX + 16 + (size_t)num_tiles(n) * RADIX; }
 
-// Sorts (keys_a, vals_a) using (keys_b, vals_b) as the alternate buffer; the result ends in the
-// `a` buffers (8 passes).  Returns the number of kernels launched.
+// Sorts (keys_a, vals_a) on the low 8 * passes key bits (keys must be zero above them) using
+// (keys_b, vals_b) as the alternate buffer.  The result ends in the `a` buffers when `passes` is even
+// and in the `b` buffers when it is odd (*in_b tells which).  Returns the number of kernels launched.
 inline int sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint64_t n,
-                      uint32_t* temp, int sm_count, cudaStream_t stream) {
+                      uint32_t* temp, int sm_count, cudaStream_t stream, int passes = PASSES, bool* in_b = nullptr) {
+  if (in_b) *in_b = false;
   if (n == 0) return 0;
+  if (passes < 1) passes = 1;
+  if (passes > PASSES) passes = PASSES;
   uint32_t* hist = temp;
   uint32_t* counters = temp + PASSES * RADIX;
   uint32_t* status = counters + 16;
@@ -202,7 +206,7 @@ inline int sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint
   int launches = 2;
   uint64_t *kin = keys_a, *kout = keys_b;
   uint32_t *vin = vals_a, *vout = vals_b;
-  for (int p = 0; p < PASSES; ++p) {
+  for (int p = 0; p < passes; ++p) {
     cudaMemsetAsync(status, 0, sizeof(uint32_t) * (size_t)tiles * RADIX, stream);
     onesweep_kernel<<<tiles, THREADS, DYN_SMEM, stream>>>(kin, vin, kout, vout, n, p * RADIX_BITS, hist + p * RADIX,
                                                           status, counters + p);
@@ -210,6 +214,7 @@ inline int sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
   }
+  if (in_b) *in_b = (passes & 1) != 0;
   return launches;
 }
 

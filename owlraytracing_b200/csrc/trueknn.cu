@@ -54,6 +54,8 @@ struct tknn_ctx {
   int keep_scratch = 1;
   int sparse_divisor = 8;
   int approx_filter = 0;
+  int morton_bits = 0;        // 0 = auto (ceil(log2 n / 3) + 8, clamped to [10, 21])
+  int built_morton_bits = 21; // what the current BVH was built with (queries are coded the same way)
   int output_chunks = 4;  // host-output pipelining: slices whose D2H overlaps the next slice's search (1 = off)
   int file_order_chunks = 4;  // same for tknn_search (file-order rows): slices by original index (1 = off)
   DevBuf chunk_queue;
@@ -351,6 +353,12 @@ int estimate_radius(tknn_ctx* c, const float4* queries, uint64_t q_begin, uint64
   }
   *out = r;
   return TKNN_OK;
+}
+
+int auto_morton_bits(uint64_t n) {
+  int lg = 0;
+  while (((uint64_t)1 << lg) < n) ++lg;
+  return std::min(21, std::max(10, (lg + 2) / 3 + 8));
 }
 
 int check_ctx(tknn_ctx* c) { return c ? TKNN_OK : TKNN_EINVAL; }
@@ -659,6 +667,10 @@ int tknn_set_option(tknn_ctx* c, int key, int64_t value) {
     case TKNN_OPT_SQUARED_DIST: c->squared = value ? 1 : 0; return TKNN_OK;
     case TKNN_OPT_KEEP_SCRATCH: c->keep_scratch = value ? 1 : 0; return TKNN_OK;
     case TKNN_OPT_APPROX_FILTER: c->approx_filter = value ? 1 : 0; return TKNN_OK;
+    case TKNN_OPT_MORTON_BITS:
+      if (value != 0 && (value < 4 || value > 21)) return fail(c, TKNN_EINVAL, "morton bits per axis must be 0 (auto) or in [4, 21]");
+      c->morton_bits = (int)value;
+      return TKNN_OK;
     case TKNN_OPT_FILE_ORDER_CHUNKS:
       if (value < 1 || value > 64) return fail(c, TKNN_EINVAL, "file-order chunks outside [1, 64]");
       c->file_order_chunks = (int)value;
@@ -753,15 +765,19 @@ int tknn_build(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int stride_fl
   TK_B(ensure(c, keys_b, n * sizeof(uint64_t)));
   TK_B(ensure(c, vals_a, n * sizeof(uint32_t)));
   TK_B(ensure(c, vals_b, n * sizeof(uint32_t)));
-  lbvh::morton_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, n, dim, stride_floats, sc + SC_BOUNDS,
+  const int mbits = c->morton_bits > 0 ? c->morton_bits : auto_morton_bits(n);
+  lbvh::morton_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, n, dim, stride_floats, sc + SC_BOUNDS, mbits,
                                                                              keys_a.as<uint64_t>(), vals_a.as<uint32_t>());
   ++launches;
   TK_BC(cudaEventRecord(c->ev[3], st));
 
   // ---- onesweep radix sort ----
   TK_B(ensure(c, sort_tmp, rsort::temp_words(n) * sizeof(uint32_t)));
+  bool sorted_in_b = false;
   launches += rsort::sort_pairs(keys_a.as<uint64_t>(), vals_a.as<uint32_t>(), keys_b.as<uint64_t>(), vals_b.as<uint32_t>(), n,
-                                sort_tmp.as<uint32_t>(), c->sm_count, st);
+                                sort_tmp.as<uint32_t>(), c->sm_count, st, (3 * mbits + 7) / 8, &sorted_in_b);
+  const uint64_t* skeys = sorted_in_b ? keys_b.as<uint64_t>() : keys_a.as<uint64_t>();
+  const uint32_t* svals = sorted_in_b ? vals_b.as<uint32_t>() : vals_a.as<uint32_t>();
   TK_BC(cudaGetLastError());
   TK_BC(cudaEventRecord(c->ev[4], st));
 
@@ -770,7 +786,7 @@ int tknn_build(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int stride_fl
   TK_B(ensure(c, delta, n));
   TK_B(ensure(c, ballots, nw * sizeof(uint32_t)));
   TK_B(ensure(c, c->offsets, (nw + 1) * sizeof(uint32_t)));
-  lbvh::delta_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(keys_a.as<uint64_t>(), n, delta.as<uint8_t>());
+  lbvh::delta_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(skeys, n, delta.as<uint8_t>());
   const uint64_t force_split = (n <= (uint64_t)c->leaf_size) ? n / 2 : 0;
   lbvh::leaf_flag_kernel<<<blocks_for(nw * 32, lbvh::THREADS), lbvh::THREADS, 0, st>>>(
       delta.as<uint8_t>(), n, c->leaf_size, c->leaf_policy, force_split, ballots.as<uint32_t>());
@@ -787,10 +803,10 @@ int tknn_build(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int stride_fl
   TK_B(ensure(c, leaf_key, (size_t)m * sizeof(uint64_t)));
   TK_B(ensure(c, c->pts, n * sizeof(float4)));
   lbvh::leaf_emit_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(
-      ballots.as<uint32_t>(), c->offsets.as<uint32_t>(), keys_a.as<uint64_t>(), n, m, c->leaf_start.as<uint32_t>(),
+      ballots.as<uint32_t>(), c->offsets.as<uint32_t>(), skeys, n, m, c->leaf_start.as<uint32_t>(),
       leaf_key.as<uint64_t>());
   lbvh::gather_points_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, dim, stride_floats,
-                                                                                   vals_a.as<uint32_t>(), n, c->pts.as<float4>());
+                                                                                   svals, n, c->pts.as<float4>());
   launches += 2;
   TK_BC(cudaEventRecord(c->ev[5], st));
 
@@ -831,6 +847,7 @@ int tknn_build(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int stride_fl
   S.n_points = n;
   S.n_leaves = m;
   S.n_nodes = m - 1;
+  c->built_morton_bits = mbits;
   S.build_launches = (uint32_t)launches;
   c->n = n;
   c->n_leaves = m;
@@ -937,25 +954,28 @@ int tknn_query(tknn_ctx* c, const float* queries, uint64_t nq, int dim, int stri
   TK_B(ensure(c, sort_tmp, rsort::temp_words(nq) * sizeof(uint32_t)));
   TK_B(ensure(c, qpts, nq * sizeof(float4)));
   int launches = 0;
-  lbvh::morton_kernel<<<blocks_for(nq, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_q, nq, dim, stride_floats, sc + SC_BOUNDS,
+  const int qbits = c->built_morton_bits;
+  lbvh::morton_kernel<<<blocks_for(nq, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_q, nq, dim, stride_floats, sc + SC_BOUNDS, qbits,
                                                                               keys_a.as<uint64_t>(), vals_a.as<uint32_t>());
   ++launches;
+  bool q_in_b = false;
   launches += rsort::sort_pairs(keys_a.as<uint64_t>(), vals_a.as<uint32_t>(), keys_b.as<uint64_t>(), vals_b.as<uint32_t>(), nq,
-                                sort_tmp.as<uint32_t>(), c->sm_count, st);
+                                sort_tmp.as<uint32_t>(), c->sm_count, st, (3 * qbits + 7) / 8, &q_in_b);
+  const uint32_t* qorder = q_in_b ? vals_b.as<uint32_t>() : vals_a.as<uint32_t>();
   lbvh::gather_points_kernel<<<blocks_for(nq, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_q, dim, stride_floats,
-                                                                                    vals_a.as<uint32_t>(), nq, qpts.as<float4>());
+                                                                                    qorder, nq, qpts.as<float4>());
   ++launches;
   const int32_t* d_sid_sorted = nullptr;
   const float* d_r2_sorted = nullptr;
   if (d_sid) {
     TK_B(ensure(c, sid_sorted, nq * sizeof(int32_t)));
-    brute::gather_i32_kernel<<<blocks_for(nq, 256), 256, 0, st>>>(d_sid, vals_a.as<uint32_t>(), nq, sid_sorted.as<int32_t>());
+    brute::gather_i32_kernel<<<blocks_for(nq, 256), 256, 0, st>>>(d_sid, qorder, nq, sid_sorted.as<int32_t>());
     d_sid_sorted = sid_sorted.as<int32_t>();
     ++launches;
   }
   if (d_rad) {
     TK_B(ensure(c, r2_sorted, nq * sizeof(float)));
-    brute::gather_r2_kernel<<<blocks_for(nq, 256), 256, 0, st>>>(d_rad, vals_a.as<uint32_t>(), nq, r2_sorted.as<float>());
+    brute::gather_r2_kernel<<<blocks_for(nq, 256), 256, 0, st>>>(d_rad, qorder, nq, r2_sorted.as<float>());
     d_r2_sorted = r2_sorted.as<float>();
     ++launches;
   }
@@ -1225,7 +1245,7 @@ int tknn_morton_codes(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int st
   TK_B(ensure(c, vals, n * sizeof(uint32_t)));
   TK_B(ensure(c, dob, sizeof(ob)));
   TK_BC(cudaMemcpyAsync(dob.p, ob, sizeof(ob), cudaMemcpyHostToDevice, st));
-  lbvh::morton_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, n, dim, stride_floats, dob.as<uint32_t>(),
+  lbvh::morton_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, n, dim, stride_floats, dob.as<uint32_t>(), 21,
                                                                              d_keys, vals.as<uint32_t>());
   TK_BC(cudaGetLastError());
   if (!out_dev) TK_BC(cudaMemcpyAsync(codes_out, d_keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
