@@ -315,12 +315,23 @@ def run_gpu(args):
         xh_np, out_np = xh.numpy(), (qid_h.numpy(), idx_h.numpy(), dst_h.numpy())
 
         full_np = (idx_h.numpy()[:n_points], dst_h.numpy()[:n_points]) if world == 1 else None
+        sh = None
+        if world > 1:
+            from owlraytracing_b200.sharded import ShardedTrueKNN
+
+            sh = ShardedTrueKNN(engine=t)
+            per = (n_points + world - 1) // world
+            my_slice = xh[rank * per: min(n_points, (rank + 1) * per)]   # this rank's 1/N of the pinned host cloud
 
         def e2e_step():
-            t.build(xh_np)                                     # H2D of the points + LBVH build
-            if world == 1 and not args.e2e_shard_api:
-                # the reference-facing call: rows in file order (tknn_search), search + D2H
-                return t.search(k, args.start_radius, out=full_np)
+            if world == 1:
+                t.build(xh_np)                                 # H2D of the points + LBVH build
+                if not args.e2e_shard_api:
+                    # the reference-facing call: rows in file order (tknn_search), search + D2H
+                    return t.search(k, args.start_radius, out=full_np)
+            else:
+                # every rank uploads 1/N of the cloud, one all_gather over NVLink replicates it, then build
+                sh.build_from_slices(my_slice, n_points, device=dev)
             return t.search_shard(k, rank, world, start_radius=args.start_radius, out=out_np)  # search + D2H
 
         if args.output_chunks > 0:
@@ -343,8 +354,10 @@ def run_gpu(args):
         if world > 1:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         e_ms = float(tm[0].item()) / e2e_steps
-        e2e = {"value": total_queries / (e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": int(n_points * 12),
-               "d2h_bytes_per_step": int(es["d2h_bytes"]), "ms_per_step": e_ms, "wall_ms_per_step": float(tm[1].item()) / e2e_steps,
+        e2e = {"value": total_queries / (e_ms * 1e-3), "unit": "queries/s",
+               "h2d_bytes_per_step": int(n_points * 12) if world == 1 else int(my_slice.shape[0] * 12),
+               "d2h_bytes_per_step": int(es["d2h_bytes"]), "ms_per_step": e_ms,
+               "h2d_note": "per rank: its 1/N slice of the points (pinned); one NCCL all_gather replicates the cloud" if world > 1 else "all points (pinned)", "wall_ms_per_step": float(tm[1].item()) / e2e_steps,
                "steps": e2e_steps, "includes": "H2D points (pinned) + LBVH build + search (all rounds) + D2H results (pinned)",
                "api": "tknn_build + tknn_search (rows in file order)" if (world == 1 and not args.e2e_shard_api)
                else "tknn_build + tknn_search_shard (compact Morton-order rows + query ids)"}

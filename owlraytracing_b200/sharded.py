@@ -39,6 +39,28 @@ class ShardedTrueKNN:
         self.n = int(points.shape[0])
         return self
 
+    def build_from_slices(self, local_points, n_total: int, device=None):
+        """Each rank holds only its contiguous 1/N slice of the cloud (host or device): upload the slice, assemble
+        the full cloud on every GPU with ONE all_gather over NVLink, then build the replicated LBVH.  Moves
+        n/N points over PCIe per rank instead of n (the only collective of the query-sharded variant, and it is
+        on the build path, not the search path)."""
+        if not torch.is_tensor(local_points):
+            local_points = torch.from_numpy(local_points)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else local_points.device
+        loc = local_points.to(device, non_blocking=True).contiguous()
+        if self.world == 1:
+            full = loc
+        else:
+            per = (n_total + self.world - 1) // self.world          # slices are ceil(n/N) rows, the last one shorter
+            pad = torch.zeros((per, loc.shape[1]), dtype=loc.dtype, device=device)
+            pad[: loc.shape[0]] = loc
+            full = torch.empty((per * self.world, loc.shape[1]), dtype=loc.dtype, device=device)
+            dist.all_gather_into_tensor(full, pad, group=self.group)
+            full = full[:n_total].contiguous() if per * self.world != n_total else full
+        self._full = full
+        return self.build(full)
+
     def search(self, k: int, start_radius: float = 0.0, gather: bool = False):
         """Local shard: (qid [m], idx [m, k], dist [m, k]).  gather=True: (idx [n, k], dist [n, k]) on every rank."""
         qid, idx, dst = self.engine.search_shard(k, self.rank, self.world, start_radius=start_radius)

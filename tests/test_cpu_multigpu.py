@@ -48,7 +48,11 @@ def _worker(rank, world, port, mode, kind, n, k, out_dir):
         if mode == "sharded":
             from owlraytracing_b200.sharded import ShardedTrueKNN
 
-            drv = ShardedTrueKNN(engine=CpuEngine()).build(x)
+            if kind == "uniform":
+                drv = ShardedTrueKNN(engine=CpuEngine()).build(x)
+            else:  # every rank contributes only its 1/N slice; one all_gather replicates the cloud
+                per = (n + world - 1) // world
+                drv = ShardedTrueKNN(engine=CpuEngine()).build_from_slices(x[rank * per: min(n, (rank + 1) * per)], n)
             qid, idx, dst = drv.search(k)
             gi, gd = drv.search(k, gather=True)
             np.savez(os.path.join(out_dir, f"r{rank}.npz"), qid=np.asarray(qid), idx=np.asarray(idx), dist=np.asarray(dst),
@@ -72,11 +76,11 @@ def _run(world, mode, kind, n, k, tmp_path):
     return [np.load(os.path.join(str(tmp_path), f"r{r}.npz")) for r in range(world)]
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_query_sharded_driver(world, oracle, tmp_path):
+@pytest.mark.parametrize("world,kind", [(2, "uniform"), (3, "uniform"), (3, "lidar")])
+def test_query_sharded_driver(world, kind, oracle, tmp_path):
     n, k = 2500, 6
-    parts = _run(world, "sharded", "uniform", n, k, tmp_path)
-    ref_i, ref_d = oracle.knn_brute(_cloud("uniform", n), k)
+    parts = _run(world, "sharded", kind, n, k, tmp_path)
+    ref_i, ref_d = oracle.knn_brute(_cloud(kind, n), k)
     seen = np.zeros(n, bool)
     for p in parts:
         assert not seen[p["qid"]].any()
