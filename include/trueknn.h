@@ -123,7 +123,9 @@ TKNN_API int tknn_create(int device, tknn_ctx** out);
 TKNN_API int tknn_destroy(tknn_ctx* ctx);
 
 /* Run all work of this context on `cuda_stream` (a cudaStream_t; NULL = the context's own
- * non-blocking stream).  The reference uses one stream per LaunchParams (owl/LaunchParams.cpp:46). */
+ * non-blocking stream; pass cudaStreamLegacy / cudaStreamPerThread for the default streams).  Inputs
+ * produced on another stream must be complete before a call: the library only orders its work on the
+ * stream it was given.  The reference uses one stream per LaunchParams (owl/LaunchParams.cpp:46). */
 TKNN_API int tknn_set_stream(tknn_ctx* ctx, void* cuda_stream);
 
 TKNN_API int tknn_set_option(tknn_ctx* ctx, int key, int64_t value);

@@ -45,6 +45,13 @@ def _box_dist2(q: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor) -> torch.Ten
     return (d * d).sum(-1)
 
 
+def _settle(t: torch.Tensor):
+    """The engine may run on a stream of its own: torch-produced inputs must be complete before it reads them.
+    (Engine calls are synchronous on return, so the other direction needs nothing.)"""
+    if t.is_cuda:
+        torch.cuda.current_stream(t.device).synchronize()
+
+
 class PartitionedTrueKNN:
     def __init__(self, engine=None, device: int | None = None, group=None):
         self.group = group
@@ -74,6 +81,7 @@ class PartitionedTrueKNN:
         self.box = torch.cat([lo, hi]).float()
         gid = torch.arange(first_index, first_index + n, dtype=torch.int64, device=dev)
         if w > 1:
+            _settle(pts)
             codes = torch.as_tensor(self.engine.morton_codes(pts, self.box.cpu())).to(dev).long()
             # splitters: evenly spaced samples of the locally sorted codes, pooled, then world-1 quantiles
             sc, _ = torch.sort(codes)
@@ -98,6 +106,7 @@ class PartitionedTrueKNN:
         self.n_owned = int(self.pts.shape[0])
         if self.n_owned < 2:
             raise ValueError("a rank owns fewer than 2 points; use fewer ranks for this cloud")
+        _settle(self.pts)
         self.engine.build(self.pts)
         # partition summary: boxes of consecutive Morton chunks of the owned points
         if w > 1:
@@ -161,7 +170,9 @@ class PartitionedTrueKNN:
             if rq.shape[0] > 0:
                 cap = torch.where(torch.isinf(rq[:, 3]), torch.full_like(rq[:, 3], -1.0), rq[:, 3]).contiguous()
                 kk = min(k, self.n_owned)
-                ri, rd = eng.query(rq[:, :3].contiguous(), kk, init_radius2=cap)
+                rq3 = rq[:, :3].contiguous()
+                _settle(rq3)
+                ri, rd = eng.query(rq3, kk, init_radius2=cap)
                 ri, rd = torch.as_tensor(ri).to(dev), torch.as_tensor(rd).to(dev)
                 if kk < k:
                     pad_i = torch.full((ri.shape[0], k - kk), -1, dtype=torch.int32, device=dev)
@@ -184,6 +195,7 @@ class PartitionedTrueKNN:
                 rows = send_rows[s]
                 ip = torch.stack([gidx[rows], bi[off:off + m]]).contiguous()
                 dp = torch.stack([d2[rows], bd[off:off + m]]).contiguous()
+                _settle(dp)
                 mi, md = eng.merge_topk(ip, dp)
                 gidx[rows] = torch.as_tensor(mi).to(dev)
                 d2[rows] = torch.as_tensor(md).to(dev)

@@ -59,6 +59,8 @@ class ShardedTrueKNN:
             dist.all_gather_into_tensor(full, pad, group=self.group)
             full = full[:n_total].contiguous() if per * self.world != n_total else full
         self._full = full
+        if full.is_cuda:
+            torch.cuda.current_stream(full.device).synchronize()  # the engine may run on a stream of its own
         return self.build(full)
 
     def search(self, k: int, start_radius: float = 0.0, gather: bool = False):

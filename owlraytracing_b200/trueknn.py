@@ -106,8 +106,18 @@ class TrueKNN:
         self._check(self._L.tknn_set_option(self._h, self._OPTS[name], int(value)))
 
     def set_stream(self, cuda_stream: int | None):
-        """Run on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
-        self._check(self._L.tknn_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        """Run on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream).
+
+        None = the context's own non-blocking stream.  0 is the LEGACY DEFAULT stream (what torch's default
+        current stream is): it is passed as cudaStreamLegacy (0x1) so that the library's work is ordered with the
+        caller's kernels and collectives on that stream instead of racing them from a private stream."""
+        if cuda_stream is None:
+            handle = 0
+        elif cuda_stream == 0:
+            handle = 1  # cudaStreamLegacy
+        else:
+            handle = cuda_stream
+        self._check(self._L.tknn_set_stream(self._h, C.c_void_p(handle)))
 
     def stats(self) -> dict:
         s = Stats()
