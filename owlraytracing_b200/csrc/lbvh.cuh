@@ -136,8 +136,10 @@ __global__ void __launch_bounds__(THREADS) delta_kernel(const uint64_t* __restri
 __global__ void __launch_bounds__(THREADS) leaf_flag_kernel(const uint8_t* __restrict__ delta, uint64_t n, int leaf_max,
                                                             int policy, uint64_t force_split,
                                                             uint32_t* __restrict__ ballots) {
-  // the block's boundaries plus a halo of MAX_LEAF on both sides, staged once in shared memory
-  __shared__ uint8_t s_delta[THREADS + 2 * MAX_LEAF];
+  // The block's boundaries plus a halo of MAX_LEAF on both sides, staged once in shared memory.  Positions
+  // outside [0, n) hold 0 = "stronger than anything" (delta[0] is 0 too), which makes the array ends behave
+  // like the boundaries at 0 and n without special cases.
+  __shared__ __align__(4) uint8_t s_delta[THREADS + 2 * MAX_LEAF];
   const int64_t block0 = (int64_t)blockIdx.x * THREADS;
   const int64_t in = (int64_t)n;
   for (int i = threadIdx.x; i < THREADS + 2 * MAX_LEAF; i += THREADS) {
@@ -146,23 +148,48 @@ __global__ void __launch_bounds__(THREADS) leaf_flag_kernel(const uint8_t* __res
   }
   __syncthreads();
   const int64_t ib = block0 + threadIdx.x;
-  const uint8_t* w = s_delta + MAX_LEAF + threadIdx.x;  // w[o] = delta[ib + o]
   bool cut = false;
   if (ib < in) {
     if (ib == 0 || (force_split && (uint64_t)ib == force_split)) cut = true;
     else if (policy == 1) cut = (ib % leaf_max) == 0;
     else {
-      const int s = w[0];
-      int64_t l = -1, r = -1;
-      const int64_t jlo = ib - leaf_max + 1;
-      for (int o = -1; ib + o >= 1 && ib + o >= jlo; --o)
-        if (w[o] < s) { l = ib + o; break; }
-      if (l < 0 && jlo <= 0) l = 0;
-      const int64_t jhi = ib + leaf_max - 1;
-      for (int o = 1; ib + o <= in - 1 && ib + o <= jhi; ++o)
-        if (w[o] < s) { r = ib + o; break; }
-      if (r < 0 && jhi >= in) r = in;
-      cut = (l < 0) || (r < 0) || (r - l > leaf_max);
+      // nearest strictly stronger boundary within leaf_max - 1 positions on each side, four bytes per step
+      const uint32_t* w32 = reinterpret_cast<const uint32_t*>(s_delta);
+      const int m = MAX_LEAF + (int)threadIdx.x;  // my position in the window
+      const uint32_t sb = (uint32_t)s_delta[m] * 0x01010101u;
+      const int none = 4 * MAX_LEAF;
+      int dl = none, dr = none;
+      {  // left: highest position p in [m - (leaf_max - 1), m - 1] with s_delta[p] < s
+        const int lo_lim = m - (leaf_max - 1);
+        int wi = (m - 1) >> 2;
+        uint32_t lt = __vcmpltu4(w32[wi], sb) & (0xFFFFFFFFu >> (8 * (3 - ((m - 1) & 3))));
+        for (;;) {
+          if (lt) {
+            const int pos = wi * 4 + ((31 - __clz(lt)) >> 3);
+            if (pos >= lo_lim) dl = m - pos;
+            break;
+          }
+          if (wi * 4 <= lo_lim) break;
+          --wi;
+          lt = __vcmpltu4(w32[wi], sb);
+        }
+      }
+      {  // right: lowest position p in [m + 1, m + (leaf_max - 1)] with s_delta[p] < s
+        const int hi_lim = m + (leaf_max - 1);
+        int wi = (m + 1) >> 2;
+        uint32_t lt = __vcmpltu4(w32[wi], sb) & (0xFFFFFFFFu << (8 * ((m + 1) & 3)));
+        for (;;) {
+          if (lt) {
+            const int pos = wi * 4 + ((__ffs(lt) - 1) >> 3);
+            if (pos <= hi_lim) dr = pos - m;
+            break;
+          }
+          if (wi * 4 + 3 >= hi_lim) break;
+          ++wi;
+          lt = __vcmpltu4(w32[wi], sb);
+        }
+      }
+      cut = dl + dr > leaf_max;  // the node that splits here spans more than leaf_max points
     }
   }
   const uint32_t word = __ballot_sync(FULL_MASK, cut);
