@@ -359,16 +359,21 @@ __global__ void __launch_bounds__(THREADS) refit_kernel(const float4* __restrict
                                                         const int32_t* __restrict__ parent_leaf,
                                                         const int32_t* __restrict__ parent_node,
                                                         uint32_t* __restrict__ arrive, Node* nodes,
+                                                        int* node_min_idx, uint32_t* __restrict__ dup_leaf_flag,
                                                         float* __restrict__ scene_box) {
   const uint32_t leaf = blockIdx.x * THREADS + threadIdx.x;
   if (leaf >= n_leaves) return;
   const uint32_t b = leaf_start[leaf], e = leaf_start[leaf + 1];
   float3 lo = make_float3(INFINITY, INFINITY, INFINITY), hi = make_float3(-INFINITY, -INFINITY, -INFINITY);
+  int mn = 0x7fffffff;  // smallest original index in the subtree (index-aware pruning of exact distance ties)
   for (uint32_t i = b; i < e; ++i) {
     const float4 p = __ldg(&pts[i]);
     lo.x = fminf(lo.x, p.x); lo.y = fminf(lo.y, p.y); lo.z = fminf(lo.z, p.z);
     hi.x = fmaxf(hi.x, p.x); hi.y = fmaxf(hi.y, p.y); hi.z = fmaxf(hi.z, p.z);
+    mn = min(mn, __float_as_int(p.w));
   }
+  // a leaf of >= 2 coincident points: the cloud has duplicate clusters; searches enable tie pruning
+  if (e - b >= 2 && lo.x == hi.x && lo.y == hi.y && lo.z == hi.z) *dup_leaf_flag = 1u;
   int32_t link = parent_leaf[leaf];
   for (;;) {
     const int node = link >> 1, slot = link & 1;
@@ -377,10 +382,12 @@ __global__ void __launch_bounds__(THREADS) refit_kernel(const float4* __restrict
     float4* rec = reinterpret_cast<float4*>(nodes + node) + 2 * slot;
     __stcg(rec, make_float4(lo.x, lo.y, lo.z, __int_as_float(ref)));
     __stcg(rec + 1, make_float4(hi.x, hi.y, hi.z, __int_as_float(cnt)));
+    __stcg(&node_min_idx[2 * node + slot], mn);
     __threadfence();
     if (atomicAdd(&arrive[node], 1u) == 0u) return;
     const float4* sib = reinterpret_cast<const float4*>(nodes + node) + 2 * (1 - slot);
     const float4 slo = __ldcg(sib), shi = __ldcg(sib + 1);
+    mn = min(mn, __ldcg(&node_min_idx[2 * node + (1 - slot)]));
     lo.x = fminf(lo.x, slo.x); lo.y = fminf(lo.y, slo.y); lo.z = fminf(lo.z, slo.z);
     hi.x = fmaxf(hi.x, shi.x); hi.y = fmaxf(hi.y, shi.y); hi.z = fmaxf(hi.z, shi.z);
     if (node == 0) {

@@ -24,6 +24,7 @@ enum Mode { MODE_KNN = 0, MODE_RANGE_COUNT = 1 };
 
 struct Params {
   const Node* nodes;
+  const int2* node_min_idx;  // per node: smallest original index under child 0 / child 1 (tie pruning)
   const float4* pts;         // sorted data points (x, y, z, original index bits)
   const float4* queries;     // query points (x, y, z, row-id bits); == pts when all points are queries
   const uint32_t* queue;     // optional list of query positions (rounds >= 2); nullptr = identity
@@ -147,6 +148,27 @@ __host__ __device__ inline size_t smem_per_warp(int k) {
   return (size_t)(k + 1) * 32 * sizeof(uint64_t) + 2 * MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int);
 }
 
+// ---- index-aware pruning of exact ties ----------------------------------------------------------
+// A child whose box distance EQUALS a lane's bound can only matter to that lane through a point at
+// exactly the k-th distance with a LOWER index than the current k-th neighbour.  So when no lane is
+// strictly inside (d < bound), the child is entered only if its smallest original index could win such
+// a tie for some lane.  Without this, a cluster of D coincident points (bound = 0, every cluster box at
+// distance 0) costs D/32 leaf visits per group — 272 ms for 400 K duplicates in a 2 M cloud; with it the
+// walk reaches the lowest-index leaf of the cluster first (child 0 first among equals) and prunes the rest
+// Queries NEAR such a cluster tie at a non-zero distance (their k nearest are k of the duplicates), so the
+// test applies to every exact tie, not only to bound == 0.  It lives in its own kernel variant (VARIANT 2),
+// selected only when the build saw a leaf of coincident points: compiled into the default variant it cost
+// 9 % on tie-free data (8.45 -> 9.2 ms on cfg2).
+template <int MODE>
+__device__ __forceinline__ bool child_wanted(float dc, float bound, int cnt, int k, const uint64_t* H, bool heap,
+                                             int child_min_idx) {
+  if (!__any_sync(FULL_MASK, dc <= bound)) return false;
+  if (MODE != MODE_KNN) return true;
+  if (__any_sync(FULL_MASK, dc < bound)) return true;
+  const bool tie_can_win = (dc == bound) && (cnt < k || child_min_idx < key_idx(kl_worst(H, k, heap)));
+  return __any_sync(FULL_MASK, tie_can_win);
+}
+
 // ---- conservative pre-filter -------------------------------------------------------------------
 // The exact test costs 6 FP instructions per (query, point).  With coordinates taken relative to a
 // group-local origin c (lane 0's query), qr = q - c and pr = p - c are small, and
@@ -169,8 +191,12 @@ __device__ __forceinline__ float prefilter_tau(float bound, float qq) {
   return (qq < 1e30f && bound < 1e30f) ? tau : INFINITY;
 }
 
-template <int MODE, bool COUNT, bool APPROX>
+// VARIANT: 0 = exact filter, 1 = conservative pre-filter (audited option), 2 = exact filter + index-aware
+// tie pruning (chosen by the host when the build found leaves of coincident points).
+template <int MODE, bool COUNT, int VARIANT>
 __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
+  constexpr bool APPROX = VARIANT == 1;
+  constexpr bool TIES = VARIANT == 2 && MODE == MODE_KNN;
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = P.k;
@@ -238,6 +264,10 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
           if (lcount <= 0) continue;
           const float dc = second ? d1 : d0;
           if (!__any_sync(FULL_MASK, dc <= bound)) continue;
+          if (TIES && !__any_sync(FULL_MASK, dc < bound)) {  // only exact ties: can any of them win?
+            const int2 mi = __ldg(&P.node_min_idx[node]);
+            if (!child_wanted<MODE>(dc, bound, cnt, k, H, heap, second ? mi.y : mi.x)) continue;
+          }
           const int start = second ? ref1 : ref0;
           float cx = 0.f, cy = 0.f, cz = 0.f;
           if (APPROX && MODE == MODE_KNN) {  // the group origin = lane 0's query (re-broadcast: saves 3 registers)
@@ -328,8 +358,13 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
       }
 
       // ---- internal children, voted against the (tightened) bounds ----
-      const bool w0 = (cnt0 == 0) && __any_sync(FULL_MASK, d0 <= bound);
-      const bool w1 = (cnt1 == 0) && __any_sync(FULL_MASK, d1 <= bound);
+      bool w0 = (cnt0 == 0) && __any_sync(FULL_MASK, d0 <= bound);
+      bool w1 = (cnt1 == 0) && __any_sync(FULL_MASK, d1 <= bound);
+      if (TIES && (w0 || w1)) {
+        const int2 mi = __ldg(&P.node_min_idx[node]);
+        if (w0) w0 = child_wanted<MODE>(d0, bound, cnt, k, H, heap, mi.x);
+        if (w1) w1 = child_wanted<MODE>(d1, bound, cnt, k, H, heap, mi.y);
+      }
       if (w0 && w1) {
         const bool far0 = __popc(__ballot_sync(FULL_MASK, d1 < d0)) > __popc(__ballot_sync(FULL_MASK, d0 < d1));
         const int nearc = far0 ? ref1 : ref0, farc = far0 ? ref0 : ref1;
@@ -438,7 +473,12 @@ __global__ void __launch_bounds__(SPARSE_THREADS) traverse_sparse_kernel(const P
         const bool second = (c == 1) != swap;
         const int lcount = second ? cnt1 : cnt0;
         if (lcount <= 0) continue;
-        if (!((second ? d1 : d0) <= bound)) continue;
+        const float dcs = second ? d1 : d0;
+        if (!(dcs <= bound)) continue;
+        if (dcs == bound && cnt == k) {  // exact tie: only a lower index can still win
+          const int2 mi = __ldg(&P.node_min_idx[node]);
+          if ((second ? mi.y : mi.x) >= key_idx(kl_worst(H, k, heap))) continue;
+        }
         const float4* lp = P.pts + (uint64_t)(uint32_t)(second ? ref1 : ref0);
         if (COUNT) c_tests += lcount;
         // four independent loads in flight per step (the tail re-reads the last point; masked off)
@@ -461,8 +501,14 @@ __global__ void __launch_bounds__(SPARSE_THREADS) traverse_sparse_kernel(const P
           }
         }
       }
-      const bool w0 = (cnt0 == 0) && (d0 <= bound);
-      const bool w1 = (cnt1 == 0) && (d1 <= bound);
+      bool w0 = (cnt0 == 0) && (d0 <= bound);
+      bool w1 = (cnt1 == 0) && (d1 <= bound);
+      if (cnt == k && ((w0 && d0 == bound) || (w1 && d1 == bound))) {
+        const int2 mi = __ldg(&P.node_min_idx[node]);
+        const int wi = key_idx(kl_worst(H, k, heap));
+        if (w0 && d0 == bound && mi.x >= wi) w0 = false;
+        if (w1 && d1 == bound && mi.y >= wi) w1 = false;
+      }
       if (w0 && w1) {
         if (sp < STACK_DEPTH) stack[sp++] = swap ? ref0 : ref1;
         else atomicOr(P.error, 1u);

@@ -44,7 +44,7 @@ struct tknn_ctx {
   // BVH
   uint64_t n = 0;
   uint32_t n_leaves = 0;
-  DevBuf pts, nodes, leaf_start;
+  DevBuf pts, nodes, leaf_start, node_min_idx;
   float scene_box[6] = {0, 0, 0, 0, 0, 0};
   // search scratch (grown on demand, kept across searches)
   DevBuf queue_a, queue_b, unresolved, offsets, block_sums, scalars, stage_idx, stage_dist, sample;
@@ -55,6 +55,7 @@ struct tknn_ctx {
   int sparse_divisor = 8;
   int approx_filter = 0;
   int morton_bits = 0;        // 0 = auto (ceil(log2 n / 3) + 8, clamped to [10, 21])
+  bool has_dup_leaves = false; // the build found a leaf of coincident points => tie-pruning kernel variant
   int built_morton_bits = 21; // what the current BVH was built with (queries are coded the same way)
   int output_chunks = 4;  // host-output pipelining: slices whose D2H overlaps the next slice's search (1 = off)
   int file_order_chunks = 4;  // same for tknn_search (file-order rows): slices by original index (1 = off)
@@ -128,7 +129,7 @@ inline unsigned blocks_for(uint64_t n, int threads) { return (unsigned)((n + thr
 
 // scalars layout (uint32 words unless noted)
 enum { SC_GROUP_COUNTER = 0, SC_TOTAL = 1, SC_ERROR = 2, SC_BOUNDS = 4 /* 7 words */, SC_SCENE = 12 /* 6 floats */,
-       SC_COUNTERS = 20 /* 8 x u64, 8-byte aligned */, SC_WORDS = 44 };
+       SC_COUNTERS = 20 /* 8 x u64, 8-byte aligned */, SC_DUPLEAF = 40, SC_WORDS = 44 };
 
 // exclusive scan of popc(words[0..nw)) into offsets, total into scalars[SC_TOTAL]
 int popc_scan(tknn_ctx* c, const uint32_t* words, uint64_t nw, uint32_t* offsets, int* launches) {
@@ -186,9 +187,11 @@ int launch_traverse(tknn_ctx* c, const trav::Params& P) {
   const uint64_t need = ((uint64_t)P.n_groups + warps - 1) / warps;
   if (grid > need) grid = std::max<uint64_t>(1, need);
   void (*kern)(const trav::Params) = nullptr;
-  const bool approx = MODE == trav::MODE_KNN && c->approx_filter;
-  if (c->counters) kern = approx ? trav::traverse_kernel<MODE, true, true> : trav::traverse_kernel<MODE, true, false>;
-  else kern = approx ? trav::traverse_kernel<MODE, false, true> : trav::traverse_kernel<MODE, false, false>;
+  const int variant = MODE != trav::MODE_KNN ? 0 : (c->has_dup_leaves ? 2 : (c->approx_filter ? 1 : 0));
+  if (c->counters) kern = variant == 2 ? trav::traverse_kernel<MODE, true, 2> : variant == 1 ? trav::traverse_kernel<MODE, true, 1>
+                                                                                            : trav::traverse_kernel<MODE, true, 0>;
+  else kern = variant == 2 ? trav::traverse_kernel<MODE, false, 2> : variant == 1 ? trav::traverse_kernel<MODE, false, 1>
+                                                                                  : trav::traverse_kernel<MODE, false, 0>;
   TK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)grid, warps * 32, smem, c->stream>>>(P);
   TK_CUDA(c, cudaGetLastError());
@@ -233,6 +236,7 @@ int run_rounds(tknn_ctx* c, const Job& job, int* launches_io) {
     trav::Params P;
     std::memset(&P, 0, sizeof(P));
     P.nodes = c->nodes.as<Node>();
+    P.node_min_idx = c->node_min_idx.as<int2>();
     P.pts = c->pts.as<float4>();
     P.queries = job.queries;
     P.queue = queue;
@@ -624,7 +628,7 @@ int tknn_destroy(tknn_ctx* c) {
   if (!c) return TKNN_EINVAL;
   ScopedDevice sd(c->device);
   cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->pts, &c->nodes, &c->leaf_start, &c->queue_a, &c->queue_b, &c->unresolved, &c->offsets,
+  for (DevBuf* b : {&c->pts, &c->nodes, &c->leaf_start, &c->node_min_idx, &c->queue_a, &c->queue_b, &c->unresolved, &c->offsets,
                     &c->block_sums, &c->scalars, &c->stage_idx, &c->stage_dist, &c->sample, &c->chunk_queue, &c->b_in, &c->b_keys_a,
                     &c->b_keys_b, &c->b_vals_a, &c->b_vals_b, &c->b_sort_tmp, &c->b_delta, &c->b_ballots, &c->b_leaf_key,
                     &c->b_child_info, &c->b_parent_leaf, &c->b_parent_node, &c->b_arrive})
@@ -812,11 +816,13 @@ int tknn_build(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int stride_fl
 
   // ---- Karras hierarchy ----
   TK_B(ensure(c, c->nodes, (size_t)(m - 1) * sizeof(Node)));
+  TK_B(ensure(c, c->node_min_idx, (size_t)(m - 1) * 2 * sizeof(int)));
   TK_B(ensure(c, child_info, (size_t)(m - 1) * sizeof(int4)));
   TK_B(ensure(c, parent_leaf, (size_t)m * sizeof(int32_t)));
   TK_B(ensure(c, parent_node, (size_t)m * sizeof(int32_t)));
   TK_B(ensure(c, arrive, (size_t)m * sizeof(uint32_t)));
   TK_BC(cudaMemsetAsync(arrive.p, 0, (size_t)m * sizeof(uint32_t), st));
+  TK_BC(cudaMemsetAsync(sc + SC_DUPLEAF, 0, sizeof(uint32_t), st));
   lbvh::karras_kernel<<<blocks_for(m - 1, lbvh::THREADS), lbvh::THREADS, 0, st>>>(
       leaf_key.as<uint64_t>(), c->leaf_start.as<uint32_t>(), m, child_info.as<int4>(), parent_leaf.as<int32_t>(),
       parent_node.as<int32_t>());
@@ -826,11 +832,14 @@ int tknn_build(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int stride_fl
   // ---- bottom-up refit ----
   lbvh::refit_kernel<<<blocks_for(m, lbvh::THREADS), lbvh::THREADS, 0, st>>>(
       c->pts.as<float4>(), c->leaf_start.as<uint32_t>(), m, child_info.as<int4>(), parent_leaf.as<int32_t>(),
-      parent_node.as<int32_t>(), arrive.as<uint32_t>(), c->nodes.as<Node>(), reinterpret_cast<float*>(sc + SC_SCENE));
+      parent_node.as<int32_t>(), arrive.as<uint32_t>(), c->nodes.as<Node>(), c->node_min_idx.as<int>(), sc + SC_DUPLEAF,
+      reinterpret_cast<float*>(sc + SC_SCENE));
   ++launches;
   TK_BC(cudaGetLastError());
   TK_BC(cudaEventRecord(c->ev[7], st));
   TK_BC(cudaMemcpyAsync(c->scene_box, sc + SC_SCENE, 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  uint32_t dupleaf = 0;
+  TK_BC(cudaMemcpyAsync(&dupleaf, sc + SC_DUPLEAF, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   TK_BC(cudaStreamSynchronize(st));
   cleanup();
 #undef TK_B
@@ -848,6 +857,7 @@ int tknn_build(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int stride_fl
   S.n_leaves = m;
   S.n_nodes = m - 1;
   c->built_morton_bits = mbits;
+  c->has_dup_leaves = dupleaf != 0;
   S.build_launches = (uint32_t)launches;
   c->n = n;
   c->n_leaves = m;
@@ -1044,6 +1054,7 @@ int tknn_range_count(tknn_ctx* c, float radius, uint32_t* count_out) {
   trav::Params P;
   std::memset(&P, 0, sizeof(P));
   P.nodes = c->nodes.as<Node>();
+  P.node_min_idx = c->node_min_idx.as<int2>();
   P.pts = c->pts.as<float4>();
   P.queries = c->pts.as<float4>();
   P.n_active = c->n;

@@ -412,3 +412,23 @@ def test_pipelined_host_output_in_file_order(knn, oracle):
         assert_knn_equal(idx, dist, *ref, f"file-order chunks={chunks}")
     idx, dist = knn.search(8, start_radius=0.02)
     assert_knn_equal(idx, dist, *ref, "file-order chunks, fixed radius")
+
+
+@pytest.mark.parametrize("k", [4, 10, 40])
+def test_big_cluster_of_coincident_points(knn, oracle, k):
+    """Sensor-style degenerate data: thousands of returns at one location.  Exactness needs the k LOWEST indices
+    of the cluster; the tie-pruning kernel variant (index-aware) keeps it fast: every query in or
+    next to the cluster ties exactly at its bound with every cluster leaf."""
+    rng = np.random.default_rng(k)
+    x = datasets.uniform(60_000, seed=31)
+    dup = rng.choice(60_000, 9_000, replace=False)          # scattered file positions, one location
+    x[dup] = x[dup[0]]
+    x[rng.choice(60_000, 50, replace=False)] = x[dup[0]] + np.float32(1e-4)   # close neighbours of the cluster
+    ref = oracle.knn_kdtree(x, k)
+    idx, dist = knn.build(x).search(k)
+    assert_knn_equal(idx, dist, *ref, f"coincident cluster k={k}")
+    st = knn.stats()
+    assert st["search_ms"] < 200.0                            # 9 000 duplicates took seconds without tie pruning
+    q = x[dup[:100]] + np.float32(3e-5)
+    qi, qd = knn.query(q, k)
+    assert_knn_equal(qi, qd, *oracle.knn_brute_queries(x, q, k), "queries next to the cluster")
