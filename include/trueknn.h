@@ -70,6 +70,8 @@ enum {
   ,TKNN_OPT_FILE_ORDER_CHUNKS = 12 /* tknn_search with HOST outputs: slices by original index (rows of a slice are
                                   contiguous and final), copies overlapped like above (default 4; 1 = off)   */
   ,TKNN_OPT_MORTON_BITS = 13   /* Morton bits per axis for the next build: 0 = auto (ceil(log2 n / 3) + 8), else 4..21 */
+  ,TKNN_OPT_TIE_PRUNING = 14   /* index-aware pruning of exact distance ties: 0 = auto (kernel variant used when the
+                                  build found leaves of coincident points), 1 = always, 2 = never           */
   ,TKNN_OPT_SPARSE_DIVISOR = 9 /* rounds >= 2 with fewer than n/divisor active queries run the
                                   thread-per-query kernel (default 8; 0 = never)                  */
 };

@@ -54,6 +54,7 @@ struct tknn_ctx {
   int keep_scratch = 1;
   int sparse_divisor = 8;
   int approx_filter = 0;
+  int tie_pruning = 0;        // 0 = auto (on when the build saw leaves of coincident points), 1 = on, 2 = off
   int morton_bits = 0;        // 0 = auto (ceil(log2 n / 3) + 8, clamped to [10, 21])
   bool has_dup_leaves = false; // the build found a leaf of coincident points => tie-pruning kernel variant
   int built_morton_bits = 21; // what the current BVH was built with (queries are coded the same way)
@@ -187,7 +188,8 @@ int launch_traverse(tknn_ctx* c, const trav::Params& P) {
   const uint64_t need = ((uint64_t)P.n_groups + warps - 1) / warps;
   if (grid > need) grid = std::max<uint64_t>(1, need);
   void (*kern)(const trav::Params) = nullptr;
-  const int variant = MODE != trav::MODE_KNN ? 0 : (c->has_dup_leaves ? 2 : (c->approx_filter ? 1 : 0));
+  const bool ties = c->tie_pruning == 1 || (c->tie_pruning == 0 && c->has_dup_leaves);
+  const int variant = MODE != trav::MODE_KNN ? 0 : (ties ? 2 : (c->approx_filter ? 1 : 0));
   if (c->counters) kern = variant == 2 ? trav::traverse_kernel<MODE, true, 2> : variant == 1 ? trav::traverse_kernel<MODE, true, 1>
                                                                                             : trav::traverse_kernel<MODE, true, 0>;
   else kern = variant == 2 ? trav::traverse_kernel<MODE, false, 2> : variant == 1 ? trav::traverse_kernel<MODE, false, 1>
@@ -671,6 +673,10 @@ int tknn_set_option(tknn_ctx* c, int key, int64_t value) {
     case TKNN_OPT_SQUARED_DIST: c->squared = value ? 1 : 0; return TKNN_OK;
     case TKNN_OPT_KEEP_SCRATCH: c->keep_scratch = value ? 1 : 0; return TKNN_OK;
     case TKNN_OPT_APPROX_FILTER: c->approx_filter = value ? 1 : 0; return TKNN_OK;
+    case TKNN_OPT_TIE_PRUNING:
+      if (value < 0 || value > 2) return fail(c, TKNN_EINVAL, "tie pruning must be 0 (auto), 1 (on) or 2 (off)");
+      c->tie_pruning = (int)value;
+      return TKNN_OK;
     case TKNN_OPT_MORTON_BITS:
       if (value != 0 && (value < 4 || value > 21)) return fail(c, TKNN_EINVAL, "morton bits per axis must be 0 (auto) or in [4, 21]");
       c->morton_bits = (int)value;
