@@ -273,6 +273,15 @@ def run_gpu(args):
     ms_per_step = elapsed_ms / args.steps
     value = total_queries / (ms_per_step * 1e-3)
 
+    clocks_hint = None
+    if sampler:
+        try:
+            vals = [float(ln.split(",")[1]) for ts, ln in sampler.lines
+                    if sampler.t_begin and sampler.t_begin - 0.05 <= ts <= (sampler.t_end or ts) + 0.15 and len(ln.split(",")) >= 9]
+            clocks_hint = float(np.median(vals)) if vals else None
+        except Exception:
+            clocks_hint = None
+
     # ---- roofline of the dominant kernel (traverse_kernel): algorithmic bytes per SURVEY.md §8d ----
     t.set_option("counters", 1)
     step()
@@ -292,6 +301,24 @@ def run_gpu(args):
             traffic = tj["dram_bytes_per_query"] * nq  # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum
         except Exception:
             traffic = None
+    # measured L2 read bandwidth of this pool's B200 (tools/measure_peaks.py) and the issue-slot view of the kernel
+    l2_peak = None
+    try:
+        l2_peak = float(json.load(open(os.path.join(ROOT, "profiles", "measured_l2_hbm_read.json")))["l2_gbs"])
+    except Exception:
+        pass
+    issue = None
+    try:
+        ij = json.load(open(os.path.join(ROOT, "profiles", "traverse_issue_profile.json")))
+        sm_count, sm_hz = 148, (clocks_hint or 1965.0) * 1e6
+        winst = ij["warp_instructions_per_query"] * nq
+        peak_issue = sm_count * 4 * sm_hz                     # one warp instruction per SMSP per cycle
+        issue = {"warp_instructions_per_query": ij["warp_instructions_per_query"], "source": ij["source"],
+                 "achieved_warp_inst_per_s": winst / (kern_ms_per_step * 1e-3), "peak_warp_inst_per_s": peak_issue,
+                 "frac": winst / (kern_ms_per_step * 1e-3) / peak_issue,
+                 "note": "instruction count from the committed ncu capture of the same kernel; time and clock measured live"}
+    except Exception:
+        pass
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "kernel": "tknn::trav::traverse_kernel", "kernel_ms_per_step": kern_ms_per_step,
@@ -299,6 +326,7 @@ def run_gpu(args):
         "algorithmic_bytes_per_query": alg_bytes / max(nq, 1),
         "bytes_per_query_loaded_once_per_warp": warp_bytes / max(nq, 1),
         "achieved_warp_shared_gbs": warp_bytes / (kern_ms_per_step * 1e-3) / 1e9,
+        "l2_peak_gbs": l2_peak, "frac_of_l2_peak": (achieved / l2_peak) if l2_peak else None, "issue_slots": issue,
         "nodes_per_query": cs["nodes_visited"] / max(nq, 1), "points_tested_per_query": cs["points_tested"] / max(nq, 1),
         "note": "SURVEY.md §8d counts every query's node/point reads; the kernel loads each once per 32-query warp and "
                 "broadcasts, so it is instruction-issue bound (ncu: issue slots ~83% busy, DRAM ~3% of peak) — see DESIGN.md",
