@@ -85,7 +85,7 @@ class PartitionedTrueKNN:
             codes = torch.as_tensor(self.engine.morton_codes(pts, self.box.cpu())).to(dev).long()
             # splitters: evenly spaced samples of the locally sorted codes, pooled, then world-1 quantiles
             sc, _ = torch.sort(codes)
-            take = torch.linspace(0, max(n - 1, 0), _SAMPLES_PER_RANK, device=dev).long()
+            take = (torch.arange(_SAMPLES_PER_RANK, device=dev, dtype=torch.int64) * max(n - 1, 0)) // (_SAMPLES_PER_RANK - 1)
             sample = sc[take] if n else torch.zeros((_SAMPLES_PER_RANK,), dtype=torch.int64, device=dev)
             pool = torch.empty((w * _SAMPLES_PER_RANK,), dtype=torch.int64, device=dev)
             dist.all_gather_into_tensor(pool, sample.contiguous(), group=self.group)
