@@ -64,6 +64,7 @@ class TrueKNN:
                                    "there is no CPU fallback")
         self._h = h
         self.device = int(device)
+        self._own_stream = True  # until set_stream() hands over a caller stream
         self.n = 0
         self._like = None
         for k, v in options.items():
@@ -112,6 +113,7 @@ class TrueKNN:
         None = the context's own non-blocking stream.  0 is the LEGACY DEFAULT stream (what torch's default
         current stream is): it is passed as cudaStreamLegacy (0x1) so that the library's work is ordered with the
         caller's kernels and collectives on that stream instead of racing them from a private stream."""
+        self._own_stream = cuda_stream is None
         if cuda_stream is None:
             handle = 0
         elif cuda_stream == 0:
@@ -119,6 +121,15 @@ class TrueKNN:
         else:
             handle = cuda_stream
         self._check(self._L.tknn_set_stream(self._h, C.c_void_p(handle)))
+
+    def _in(self, a):
+        """Pointer of an INPUT array.  While the context runs on its own stream, a CUDA tensor produced by
+        torch on another stream must be complete before the library reads it: settle torch's current stream."""
+        if a is not None and _is_tensor(a) and a.is_cuda and self._own_stream:
+            import torch
+
+            torch.cuda.current_stream(a.device).synchronize()
+        return _ptr(a)
 
     def stats(self) -> dict:
         s = Stats()
@@ -143,7 +154,7 @@ class TrueKNN:
         stride = int(points.shape[1])
         if dim is None:
             dim = min(stride, 3)
-        self._check(self._L.tknn_build(self._h, _ptr(points), int(points.shape[0]), int(dim), stride))
+        self._check(self._L.tknn_build(self._h, self._in(points), int(points.shape[0]), int(dim), stride))
         self.n = int(points.shape[0])
         self._like = points
         return self
@@ -198,7 +209,7 @@ class TrueKNN:
             init_radius2 = np.ascontiguousarray(init_radius2, dtype=np.float32)
         idx = self._out(queries, nq, k, np.int32)
         dist = self._out(queries, nq, k, np.float32)
-        self._check(self._L.tknn_query(self._h, _ptr(queries), nq, int(dim), stride, _ptr(self_ids), _ptr(init_radius2), int(k),
+        self._check(self._L.tknn_query(self._h, self._in(queries), nq, int(dim), stride, self._in(self_ids), self._in(init_radius2), int(k),
                                        C.c_float(start_radius), _ptr(idx), _ptr(dist)))
         return idx, dist
 
@@ -225,7 +236,7 @@ class TrueKNN:
         nq = int(query_ids.shape[0])
         idx = self._out(query_ids, nq, k, np.int32)
         dist = self._out(query_ids, nq, k, np.float32)
-        self._check(self._L.tknn_brute_force(self._h, _ptr(query_ids), nq, int(k), _ptr(idx), _ptr(dist)))
+        self._check(self._L.tknn_brute_force(self._h, self._in(query_ids), nq, int(k), _ptr(idx), _ptr(dist)))
         return idx, dist
 
     def merge_topk(self, idx_parts, d2_parts):
@@ -233,13 +244,13 @@ class TrueKNN:
         parts, nq, k = (int(x) for x in idx_parts.shape)
         idx = self._out(idx_parts, nq, k, np.int32)
         dist = self._out(idx_parts, nq, k, np.float32)
-        self._check(self._L.tknn_merge_topk(self._h, _ptr(idx_parts), _ptr(d2_parts), parts, nq, k, _ptr(idx), _ptr(dist)))
+        self._check(self._L.tknn_merge_topk(self._h, self._in(idx_parts), self._in(d2_parts), parts, nq, k, _ptr(idx), _ptr(dist)))
         return idx, dist
 
     # ---- introspection (tests / bench) ----
     def sort_pairs(self, keys, values):
         n = int(keys.shape[0])
-        self._check(self._L.tknn_sort_pairs(self._h, _ptr(keys), _ptr(values), n))
+        self._check(self._L.tknn_sort_pairs(self._h, self._in(keys), self._in(values), n))
         return keys, values
 
     def get_bvh(self):
@@ -266,7 +277,7 @@ class TrueKNN:
         else:
             out = np.empty((n,), np.uint64)
             box = np.ascontiguousarray(box6, dtype=np.float32)
-        self._check(self._L.tknn_morton_codes(self._h, _ptr(points), n, int(dim), stride, _ptr(box), _ptr(out)))
+        self._check(self._L.tknn_morton_codes(self._h, self._in(points), n, int(dim), stride, _ptr(box), _ptr(out)))
         return out
 
     def generate_uniform(self, seed: int, first: int, n: int, out=None):

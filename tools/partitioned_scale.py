@@ -40,6 +40,12 @@ def main():
     drv.build(x, lo)
     dist.barrier(); torch.cuda.synchronize()
     t1 = time.perf_counter()
+    # integrity of the redistribution: every global id owned exactly once
+    g = drv.gid
+    own = torch.tensor([g.numel(), int(g.min().item()), int(g.max().item()), int((g[1:] == g[:-1]).sum().item())], device=dev)
+    tot = own.clone(); dist.all_reduce(tot)
+    if rank == 0:
+        print("owned/min/max/dups on rank 0:", own.tolist(), "total owned:", int(tot[0].item()), "total dups:", int(tot[3].item()), flush=True)
     gid, idx, dst = drv.search(k)
     dist.barrier(); torch.cuda.synchronize()
     t2 = time.perf_counter()
