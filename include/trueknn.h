@@ -207,6 +207,14 @@ TKNN_API int tknn_get_bvh(const tknn_ctx* ctx, void* nodes_out, void* points_out
 TKNN_API int tknn_morton_codes(tknn_ctx* ctx, const float* xyz, uint64_t n, int dim, int stride_floats,
                                const float* box6, uint64_t* codes_out);
 
+/* Point-partitioned driver: for each of n points with squared reach reach2[i], the set of
+ * REMOTE ranks whose published per-cell boxes the closed ball (p, sqrt(reach2)) touches, as a bit mask
+ * (bit s = rank s, n_ranks <= 32).  summaries: [n_ranks][8^cell_bits][6] floats (lo.xyz, hi.xyz; an
+ * untouched cell holds an inverted box); box6: the global box the Morton grid spans.  Device arrays. */
+TKNN_API int tknn_reach_mask(tknn_ctx* ctx, const float* xyz, uint64_t n, int stride_floats, const float* reach2,
+                             const float* box6, const float* summaries, int n_ranks, int cell_bits, int self_rank,
+                             uint32_t* mask_out);
+
 /* Synthetic clouds generated on the device by the stateless hash of SURVEY.md §8d:
  * u(i,a) = (mix64(seed ^ ((3i+a) * 0x9E3779B97F4A7C15)) >> 40) * 2^-24.  Writes n rows of xyz
  * for indices [first, first+n) to a DEVICE or HOST array. */

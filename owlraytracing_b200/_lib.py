@@ -76,7 +76,7 @@ EXPORTS = [
     "tknn_search_shard", "tknn_shard_capacity", "tknn_query", "tknn_range_count", "tknn_estimate_start_radius",
     "tknn_brute_force", "tknn_merge_topk", "tknn_get_stats", "tknn_last_error", "tknn_version", "tknn_sort_pairs",
     "tknn_get_bvh", "tknn_generate_uniform", "tknn_measure_bandwidth", "tknn_morton_codes",
-    "tknn_read_points", "tknn_write_neighbours",
+    "tknn_read_points", "tknn_write_neighbours", "tknn_reach_mask",
 ]
 
 _lib = None
@@ -115,6 +115,7 @@ def load() -> C.CDLL:
     L.tknn_get_bvh.argtypes = [vp, vp, vp, vp]
     L.tknn_generate_uniform.argtypes = [vp, u64, u64, u64, vp]
     L.tknn_morton_codes.argtypes = [vp, vp, u64, C.c_int, C.c_int, vp, vp]
+    L.tknn_reach_mask.argtypes = [vp, vp, u64, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
     L.tknn_read_points.argtypes = [C.c_char_p, u64, C.c_int, vp, u64, C.POINTER(u64)]
     L.tknn_write_neighbours.argtypes = [C.c_char_p, vp, vp, u64, C.c_int, C.c_int]
     L.tknn_measure_bandwidth.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int),

@@ -174,6 +174,54 @@ __global__ void __launch_bounds__(256) gather_r2_kernel(const float* __restrict_
   }
 }
 
+// Point-partitioned driver: which remote ranks can the closed ball (q, sqrt(reach2)) reach?  Every rank
+// publishes the tight box of its points inside each top-level Morton cell (2^bits cells per axis on the
+// global cubic grid, cell id = the top 3*bits bits of the Morton code).  A ball only touches the cells
+// between the cells of its two extreme corners — computed with the builder's own monotone quantiser, so
+// no point of the ball can lie in a cell outside that range — usually 1..8 of them.  mask bit s = rank s.
+__global__ void __launch_bounds__(256) reach_mask_kernel(const float* __restrict__ xyz, uint64_t n, int stride,
+                                                         const float* __restrict__ reach2, const float* __restrict__ box6,
+                                                         const float* __restrict__ summ, int n_ranks, int bits, int self_rank,
+                                                         uint32_t* __restrict__ mask_out) {
+  const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float lx = box6[0], ly = box6[1], lz = box6[2];
+  const float ext = fmaxf(fmaxf(box6[3] - lx, box6[4] - ly), fmaxf(box6[5] - lz, FLT_MIN));
+  const float scale = 2097152.0f / ext;  // identical to morton_kernel
+  const float* p = xyz + i * (uint64_t)stride;
+  const float qx = p[0], qy = p[1], qz = p[2];
+  const float r2 = reach2[i];
+  const int cells = 1 << bits, shift = 21 - bits;
+  int c0[3] = {0, 0, 0}, c1[3] = {cells - 1, cells - 1, cells - 1};
+  const float rho = __fmul_rn(__fsqrt_ru(r2), 1.000001f);
+  if (rho < 1e30f) {
+    const float q[3] = {qx, qy, qz}, l[3] = {lx, ly, lz};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      c0[a] = (int)((uint32_t)fminf(fmaxf((__fsub_rd(q[a], rho) - l[a]) * scale, 0.0f), 2097151.0f) >> shift);
+      c1[a] = (int)((uint32_t)fminf(fmaxf((__fadd_ru(q[a], rho) - l[a]) * scale, 0.0f), 2097151.0f) >> shift);
+    }
+  }
+  const float lim = __fmaf_rn(r2, 1e-5f, r2) + 1e-30f;  // the boxes are tested in plain fp32: widen a little
+  uint32_t mask = 0;
+  for (int cz = c0[2]; cz <= c1[2]; ++cz)
+    for (int cy = c0[1]; cy <= c1[1]; ++cy)
+      for (int cx = c0[0]; cx <= c1[0]; ++cx) {
+        uint32_t cell = 0;  // Morton interleave of the cell coordinates: x bit highest, then y, then z
+        for (int b = 0; b < bits; ++b)
+          cell |= (((uint32_t)cx >> b) & 1u) << (3 * b + 2) | (((uint32_t)cy >> b) & 1u) << (3 * b + 1) | (((uint32_t)cz >> b) & 1u) << (3 * b);
+        for (int s = 0; s < n_ranks; ++s) {
+          if (s == self_rank || ((mask >> s) & 1u)) continue;
+          const float* bx = summ + ((size_t)s * ((size_t)1 << (3 * bits)) + cell) * 6;
+          const float dx = fmaxf(fmaxf(bx[0] - qx, qx - bx[3]), 0.0f);
+          const float dy = fmaxf(fmaxf(bx[1] - qy, qy - bx[4]), 0.0f);
+          const float dz = fmaxf(fmaxf(bx[2] - qz, qz - bx[5]), 0.0f);
+          if (dx * dx + dy * dy + dz * dz <= lim) mask |= 1u << s;  // an empty (inverted) box gives +inf
+        }
+      }
+  mask_out[i] = mask;
+}
+
 // u(i, a) = (mix64(seed ^ ((3 i + a) * phi64)) >> 40) * 2^-24  in [0, 1)   
 __global__ void __launch_bounds__(256) generate_uniform_kernel(uint64_t seed, uint64_t first, uint64_t n,
                                                                float* __restrict__ xyz) {

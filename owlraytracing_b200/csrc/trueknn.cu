@@ -1273,6 +1273,24 @@ int tknn_morton_codes(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int st
   return TKNN_OK;
 }
 
+int tknn_reach_mask(tknn_ctx* c, const float* xyz, uint64_t n, int stride_floats, const float* reach2, const float* box6,
+                    const float* summaries, int n_ranks, int cell_bits, int self_rank, uint32_t* mask_out) {
+  TK_TRY(check_ctx(c));
+  if (n == 0) return TKNN_OK;
+  if (!xyz || !reach2 || !box6 || !summaries || !mask_out) return fail(c, TKNN_EINVAL, "null array");
+  if (n_ranks < 1 || n_ranks > 32 || cell_bits < 1 || cell_bits > 5 || stride_floats < 3)
+    return fail(c, TKNN_EINVAL, "n_ranks in [1,32], cell_bits in [1,5], stride >= 3");
+  if (!is_device_ptr(xyz) || !is_device_ptr(reach2) || !is_device_ptr(box6) || !is_device_ptr(summaries) ||
+      !is_device_ptr(mask_out))
+    return fail(c, TKNN_EINVAL, "tknn_reach_mask takes device arrays");
+  ScopedDevice sd(c->device);
+  brute::reach_mask_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(xyz, n, stride_floats, reach2, box6, summaries, n_ranks,
+                                                                     cell_bits, self_rank, mask_out);
+  TK_CUDA(c, cudaGetLastError());
+  TK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return TKNN_OK;
+}
+
 int tknn_generate_uniform(tknn_ctx* c, uint64_t seed, uint64_t first, uint64_t n, float* xyz_out) {
   TK_TRY(check_ctx(c));
   if (n == 0) return TKNN_OK;

@@ -10,7 +10,7 @@ kNN of the points it OWNS after redistribution by Morton range:
           4. redistribution               all_to_all of (x, y, z, global id) by Morton range
           5. local LBVH                   tknn_build on the owned points, ordered by global id so that
                                           the local lowest-index tie-break IS the global one
-          6. partition summaries          <= 256 boxes of consecutive Morton chunks per rank, all_gather
+          6. partition summaries          tight boxes of the owned points per top-level Morton cell (<= 512), all_gather
   search  7. local all-points kNN         tknn_search (squared distances)
           8. boundary queries             a query goes to rank s iff its ball (q, d_k) reaches one of s's
                                           summary boxes (conservative test)
@@ -25,7 +25,8 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-_SUMMARY_BOXES = 256
+_SUMMARY_BITS = 9                      # summaries live on the 8 x 8 x 8 grid of top-level Morton cells
+_SUMMARY_BOXES = 1 << _SUMMARY_BITS    # <= 512 occupied cells per rank
 _SAMPLES_PER_RANK = 1024
 
 
@@ -108,19 +109,20 @@ class PartitionedTrueKNN:
             raise ValueError("a rank owns fewer than 2 points; use fewer ranks for this cloud")
         _settle(self.pts)
         self.engine.build(self.pts)
-        # partition summary: boxes of consecutive Morton chunks of the owned points
+        # Partition summary: the tight box of the owned points inside every top-level Morton cell (9 code bits =
+        # the 8 x 8 x 8 grid of the global cube) this rank touches.  Cells are disjoint cubes and a rank's Morton
+        # range is a run of whole cells plus at most two partial ones, so the boxes of different ranks only
+        # overlap inside those shared end cells — chunks of consecutive points (the first version) straddled
+        # Z-curve jumps and made 29 % of the queries "boundary" at 8 ranks.
         if w > 1:
             codes = torch.as_tensor(self.engine.morton_codes(self.pts, self.box.cpu())).to(dev).long()
-            so = torch.argsort(codes)
-            c = min(_SUMMARY_BOXES, self.n_owned)
-            edges = (torch.arange(c + 1, device=dev) * self.n_owned) // c
-            sp = self.pts[so]
+            cell = codes >> (63 - _SUMMARY_BITS)
             lo_b = torch.full((_SUMMARY_BOXES, 3), float("inf"), device=dev)
             hi_b = torch.full((_SUMMARY_BOXES, 3), float("-inf"), device=dev)
-            seg = torch.bucketize(torch.arange(self.n_owned, device=dev), edges[1:], right=True)
-            lo_b[:c] = torch.full((c, 3), float("inf"), device=dev).scatter_reduce(0, seg.view(-1, 1).expand(-1, 3), sp, "amin")
-            hi_b[:c] = torch.full((c, 3), float("-inf"), device=dev).scatter_reduce(0, seg.view(-1, 1).expand(-1, 3), sp, "amax")
-            mine = torch.cat([lo_b, hi_b], 1).contiguous()            # [256, 6]; unused boxes are inverted (never hit)
+            ix = cell.view(-1, 1).expand(-1, 3)
+            lo_b.scatter_reduce_(0, ix, self.pts, "amin")
+            hi_b.scatter_reduce_(0, ix, self.pts, "amax")
+            mine = torch.cat([lo_b, hi_b], 1).contiguous()            # [512, 6]; untouched cells stay inverted (never hit)
             allb = torch.empty((w * _SUMMARY_BOXES, 6), dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(allb, mine, group=self.group)
             self.summ = allb.view(w, _SUMMARY_BOXES, 6)
@@ -132,40 +134,42 @@ class PartitionedTrueKNN:
 
         Returns (gid [m] int64, idx [m,k] int32 global neighbour indices, dist [m,k] float32)."""
         w, dev, eng = self.world, self.pts.device, self.engine
+        import time as _time
+
+        def _tick():
+            if dev.type == "cuda":
+                torch.cuda.synchronize(dev)
+            return _time.perf_counter()
+
+        t_0 = _tick()
         idx, d2 = eng.search(k, start_radius)
         idx, d2 = torch.as_tensor(idx).to(dev), torch.as_tensor(d2).to(dev)
         g32 = self.gid.to(torch.int32)
         gidx = torch.where(idx >= 0, g32[idx.clamp(min=0).long()], idx)
+        t_local = _tick()
         self.stats = {"owned": self.n_owned, "boundary_sent": 0, "boundary_received": 0}
+        t_detect = t_exchange = t_remote = t_merge = t_local
         if w > 1:
             inf = torch.full((), float("inf"), device=dev)
             dk2 = torch.where(idx[:, k - 1] >= 0, d2[:, k - 1], inf)  # unfilled list: unbounded ball
-            # conservative reach test (torch arithmetic is not the kernels' fmaf chain: widen a little)
-            reach = dk2 * (1.0 + 1e-5) + 1e-30
+            reach = dk2  # the reach kernel widens it a little itself (its box test is plain fp32)
+            # which remote ranks can each query's ball reach?  (tknn_reach_mask: <= 8 neighbouring cells per query)
+            mask = eng.reach_mask(self.pts, reach.contiguous(), self.box, self.summ, self.rank, _SUMMARY_BITS // 3)
+            mask = torch.as_tensor(mask).to(dev)
             send_rows, send_counts = [], []
             for s in range(w):
-                if s == self.rank:
-                    send_rows.append(torch.empty((0,), dtype=torch.int64, device=dev))
-                    send_counts.append(0)
-                    continue
-                lo_s, hi_s = self.summ[s, :, :3], self.summ[s, :, 3:]
-                whole = _box_dist2(self.pts, lo_s.amin(0), hi_s.amax(0)) <= reach
-                cand = torch.nonzero(whole).view(-1)
-                hit = torch.zeros((cand.numel(),), dtype=torch.bool, device=dev)
-                for c0 in range(0, cand.numel(), 1 << 16):
-                    cc = cand[c0:c0 + (1 << 16)]
-                    bd = _box_dist2(self.pts[cc].view(-1, 1, 3), lo_s.view(1, -1, 3), hi_s.view(1, -1, 3))
-                    hit[c0:c0 + cc.numel()] = (bd <= reach[cc].view(-1, 1)).any(1)
-                rows = cand[hit]
+                rows = torch.nonzero((mask >> s) & 1).view(-1) if s != self.rank else torch.empty((0,), dtype=torch.int64, device=dev)
                 send_rows.append(rows)
                 send_counts.append(int(rows.numel()))
             rows_all = torch.cat(send_rows)
+            t_detect = _tick()
             sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
             self.stats["boundary_sent"] = int(rows_all.numel())
             # query payload: x, y, z, d_k^2
             payload = torch.cat([self.pts[rows_all], dk2[rows_all].view(-1, 1)], 1)
             rq, rc = _all_to_all_rows(payload, sc, self.group)
             self.stats["boundary_received"] = int(rq.shape[0])
+            t_exchange = _tick()
             # remote search: closed cap at the asker's k-th d2; local indices -> global
             if rq.shape[0] > 0:
                 cap = torch.where(torch.isinf(rq[:, 3]), torch.full_like(rq[:, 3], -1.0), rq[:, 3]).contiguous()
@@ -182,6 +186,7 @@ class PartitionedTrueKNN:
             else:
                 rgi = torch.empty((0, k), dtype=torch.int32, device=dev)
                 rd = torch.empty((0, k), dtype=torch.float32, device=dev)
+            t_remote = _tick()
             # answers travel back along the same routes
             ans = torch.cat([rgi.view(torch.float32), rd], 1)
             back, _ = _all_to_all_rows(ans, rc, self.group)
@@ -200,5 +205,10 @@ class PartitionedTrueKNN:
                 gidx[rows] = torch.as_tensor(mi).to(dev)
                 d2[rows] = torch.as_tensor(md).to(dev)
                 off += m
+            t_merge = _tick()
         dist_out = torch.where(gidx >= 0, torch.sqrt(d2), d2)
+        t_end = _tick()
+        self.stats["phase_s"] = {"local_search": t_local - t_0, "boundary_detect": t_detect - t_local,
+                                 "exchange_out": t_exchange - t_detect, "remote_search": t_remote - t_exchange,
+                                 "return_and_merge": t_merge - t_remote, "finish": t_end - t_merge}
         return self.gid, gidx, dist_out

@@ -280,6 +280,19 @@ class TrueKNN:
         self._check(self._L.tknn_morton_codes(self._h, self._in(points), n, int(dim), stride, _ptr(box), _ptr(out)))
         return out
 
+    def reach_mask(self, points, reach2, box6, summaries, self_rank: int, cell_bits: int = 3):
+        """Bit mask of the remote ranks whose per-cell summary boxes the ball (p, sqrt(reach2)) touches (CUDA tensors)."""
+        import torch
+
+        n, stride = int(points.shape[0]), int(points.shape[1])
+        n_ranks = int(summaries.shape[0])
+        box = torch.as_tensor(box6, dtype=torch.float32, device=points.device).contiguous()
+        summ = summaries.contiguous()
+        out = torch.empty((n,), dtype=torch.int32, device=points.device)
+        self._check(self._L.tknn_reach_mask(self._h, self._in(points), n, stride, self._in(reach2.contiguous()), self._in(box),
+                                            self._in(summ), n_ranks, int(cell_bits), int(self_rank), _ptr(out)))
+        return out
+
     def generate_uniform(self, seed: int, first: int, n: int, out=None):
         if out is None:
             out = np.empty((n, 3), np.float32)

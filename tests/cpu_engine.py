@@ -78,6 +78,24 @@ class CpuEngine:
                 od[q, i] = d if self.squared else np.sqrt(d)
         return torch.from_numpy(oi), torch.from_numpy(od)
 
+    def reach_mask(self, points, reach2, box6, summaries, self_rank, cell_bits=3):
+        """numpy stand-in of tknn_reach_mask: every cell of every remote rank (no neighbour-cell shortcut)."""
+        p = np.asarray(points, dtype=np.float64)
+        r2 = np.asarray(reach2, dtype=np.float64)
+        summ = np.asarray(summaries, dtype=np.float64)
+        mask = np.zeros(p.shape[0], np.int32)
+        lim = r2 * (1 + 1e-5) + 1e-30
+        for s in range(summ.shape[0]):
+            if s == self_rank:
+                continue
+            lo, hi = summ[s, :, :3], summ[s, :, 3:]
+            ok = np.isfinite(lo[:, 0]) & (lo[:, 0] <= hi[:, 0])
+            lo, hi = lo[ok], hi[ok]
+            d = np.maximum(np.maximum(lo[None] - p[:, None], p[:, None] - hi[None]), 0.0)
+            hit = ((d * d).sum(-1) <= lim[:, None]).any(1) if lo.shape[0] else np.zeros(p.shape[0], bool)
+            mask |= hit.astype(np.int32) << s
+        return torch.from_numpy(mask)
+
     # query-sharded interface: contiguous slices of a Morton-ish order in groups of 32
     def shard_capacity(self, n_shards):
         groups = (self.n + 31) // 32

@@ -432,3 +432,39 @@ def test_big_cluster_of_coincident_points(knn, oracle, k):
     q = x[dup[:100]] + np.float32(3e-5)
     qi, qd = knn.query(q, k)
     assert_knn_equal(qi, qd, *oracle.knn_brute_queries(x, q, k), "queries next to the cluster")
+
+
+def test_reach_mask_kernel_is_conservative_and_tight(knn):
+    """tknn_reach_mask (boundary-query routing of the point-partitioned driver): never misses a rank whose
+    summary box the ball really touches, and flags nothing the all-cells reference would not."""
+    import torch
+
+    rng = np.random.default_rng(12)
+    w, bits = 5, 3
+    x = datasets.lidar_like(40_000, seed=21)
+    box = np.concatenate([x.min(0), x.max(0)]).astype(np.float32)
+    codes = knn.morton_codes(x, box).astype(np.int64)
+    owner = rng.integers(0, w, x.shape[0])
+    cell = codes >> (63 - 3 * bits)
+    summ = np.empty((w, 1 << (3 * bits), 6), np.float32)
+    summ[:, :, :3], summ[:, :, 3:] = np.inf, -np.inf
+    for s in range(w):
+        for c in np.unique(cell[owner == s]):
+            p = x[(owner == s) & (cell == c)]
+            summ[s, c, :3], summ[s, c, 3:] = p.min(0), p.max(0)
+    q = x[rng.choice(x.shape[0], 5000, replace=False)]
+    r2 = (rng.random(5000).astype(np.float32) * 3.0) ** 2
+    r2[:50] = np.inf
+    r2[50:100] = 0.0
+    got = knn.reach_mask(torch.from_numpy(q).cuda(), torch.from_numpy(r2).cuda(), box, torch.from_numpy(summ).cuda(), 2, bits)
+    got = got.cpu().numpy()
+    p64, lo, hi = q.astype(np.float64)[:, None, None, :], summ[None, :, :, :3].astype(np.float64), summ[None, :, :, 3:].astype(np.float64)
+    with np.errstate(invalid="ignore"):
+        d2 = (np.maximum(np.maximum(lo - p64, p64 - hi), 0.0) ** 2).sum(-1)           # [nq, w, cells]
+    d2 = np.where(np.isnan(d2), np.inf, d2)
+    exact = (d2 <= r2.astype(np.float64)[:, None, None]).any(-1)
+    loose = (d2 <= (r2.astype(np.float64) * (1 + 1e-4) + 1e-20)[:, None, None]).any(-1)
+    exact[:, 2] = loose[:, 2] = False                                                 # never the asking rank itself
+    bits_got = ((got[:, None] >> np.arange(w)[None]) & 1).astype(bool)
+    assert (bits_got | ~exact).all(), "a reachable rank was missed"
+    assert (~bits_got | loose).all(), "a rank out of reach was flagged"

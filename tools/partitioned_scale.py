@@ -69,6 +69,8 @@ def main():
         bi, bd = ver.brute_force(ids, k)
         ok = bool(torch.equal(bi, idx[pick]) and torch.allclose(bd, dst[pick], rtol=1e-6, atol=0))
         ver.close()
+    all_phases = [None] * world
+    dist.all_gather_object(all_phases, {a: round(b, 4) for a, b in stats.get("phase_s", {}).items()})
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
@@ -76,7 +78,8 @@ def main():
                           "search_s": round(t3 - t2, 3), "queries_per_s": n_total / (t3 - t2),
                           "boundary_queries": int(sent[0].item()), "boundary_fraction": float(sent[0].item()) / n_total,
                           "verified_samples_per_rank": samples, "verified_ok": bool(flag.item()),
-                          "torch_peak_alloc_gb_rank0": round(peak_gb, 2)}), flush=True)
+                          "torch_peak_alloc_gb_rank0": round(peak_gb, 2),
+                          "phase_s_per_rank": all_phases}), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if not bool(flag.item()):
