@@ -52,11 +52,14 @@ struct Params {
                                  // [6] pre-filter violations (must stay 0)
 };
 
-// ---- bounded max-heap of u64 keys in shared memory, slot s of lane l at H[s * 32 + l] ----------
+// ---- bounded 4-ary max-heap of u64 keys in shared memory, slot s of lane l at H[s * 32 + l] ----
+// Four children per node: k = 64 is three levels deep instead of six, and the four child loads of a level
+// are independent, so an insert costs three shared-memory latencies instead of six (the binary heap left
+// the k = 64 kernel latency bound: issue slots 42 % busy at 12 resident warps per SM).
 __device__ __forceinline__ void heap_push(uint64_t* H, int& cnt, uint64_t key) {
   int i = cnt++;
   while (i > 0) {
-    const int par = (i - 1) >> 1;
+    const int par = (i - 1) >> 2;
     const uint64_t pk = H[par * 32];
     if (pk >= key) break;
     H[i * 32] = pk;
@@ -69,16 +72,20 @@ __device__ __forceinline__ void heap_push(uint64_t* H, int& cnt, uint64_t key) {
 __device__ __forceinline__ void heap_sift_root(uint64_t* H, int size, uint64_t key) {
   int i = 0;
   for (;;) {
-    int c = 2 * i + 1;
+    const int c = 4 * i + 1;
     if (c >= size) break;
-    uint64_t ck = H[c * 32];
-    if (c + 1 < size) {
-      const uint64_t ck2 = H[(c + 1) * 32];
-      if (ck2 > ck) { ck = ck2; ++c; }
-    }
-    if (ck <= key) break;
-    H[i * 32] = ck;
-    i = c;
+    const uint64_t k0 = H[c * 32];
+    const uint64_t k1 = (c + 1 < size) ? H[(c + 1) * 32] : 0ull;  // 0 never beats a real child
+    const uint64_t k2 = (c + 2 < size) ? H[(c + 2) * 32] : 0ull;
+    const uint64_t k3 = (c + 3 < size) ? H[(c + 3) * 32] : 0ull;
+    int m = c;
+    uint64_t mk = k0;
+    if (k1 > mk) { mk = k1; m = c + 1; }
+    if (k2 > mk) { mk = k2; m = c + 2; }
+    if (k3 > mk) { mk = k3; m = c + 3; }
+    if (mk <= key) break;
+    H[i * 32] = mk;
+    i = m;
   }
   H[i * 32] = key;
 }
@@ -108,8 +115,8 @@ __device__ __forceinline__ void list_insert(uint64_t* L, int& cnt, int k, uint64
   }
 }
 
-// k-list policy: ascending list for small k (short shifts, no sort at emit), binary max-heap above
-// (O(log k) per insert; heap-sorted at emit).  Warp-uniform choice.
+// k-list policy: ascending list for small k (short shifts, no sort at emit), 4-ary max-heap above
+// (O(log4 k) per insert; heap-sorted at emit).  Warp-uniform choice.
 constexpr int LIST_MAX_K = 24;
 
 // H = sentinel slot of the lane's region; the heap (large k) uses slots 1..k as its 0-based array
