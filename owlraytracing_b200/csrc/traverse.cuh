@@ -200,14 +200,15 @@ __device__ __forceinline__ float prefilter_tau(float bound, float qq) {
 
 // VARIANT: 0 = exact filter, 1 = conservative pre-filter (audited option), 2 = exact filter + index-aware
 // tie pruning (chosen by the host when the build found leaves of coincident points).
-template <int MODE, bool COUNT, int VARIANT>
+// HEAP: k > LIST_MAX_K (compile-time, so the small-k kernel does not carry the heap code).
+template <int MODE, bool COUNT, int VARIANT, bool HEAP>
 __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
   constexpr bool APPROX = VARIANT == 1;
   constexpr bool TIES = VARIANT == 2 && MODE == MODE_KNN;
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = P.k;
-  const bool heap = k > LIST_MAX_K;
+  constexpr bool heap = HEAP;
   unsigned char* wbase = smem + (size_t)warp * smem_per_warp(MODE == MODE_KNN ? k : 0);
   float4* stage = reinterpret_cast<float4*>(wbase);
   int* stack = reinterpret_cast<int*>(wbase + MAX_LEAF * sizeof(float4));
@@ -335,7 +336,8 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
                 }
                 mask |= m8 << j0;
               }
-              for (; j0 < lcount; ++j0) {
+#pragma unroll 1
+              for (; j0 < lcount; ++j0) {  // not unrolled: code size matters more here than the few tail tests
                 const float4 p = stage[j0];
                 const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
                 if (d <= bound) mask |= (1u << j0);

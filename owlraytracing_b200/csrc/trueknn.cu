@@ -190,10 +190,11 @@ int launch_traverse(tknn_ctx* c, const trav::Params& P) {
   void (*kern)(const trav::Params) = nullptr;
   const bool ties = c->tie_pruning == 1 || (c->tie_pruning == 0 && c->has_dup_leaves);
   const int variant = MODE != trav::MODE_KNN ? 0 : (ties ? 2 : (c->approx_filter ? 1 : 0));
-  if (c->counters) kern = variant == 2 ? trav::traverse_kernel<MODE, true, 2> : variant == 1 ? trav::traverse_kernel<MODE, true, 1>
-                                                                                            : trav::traverse_kernel<MODE, true, 0>;
-  else kern = variant == 2 ? trav::traverse_kernel<MODE, false, 2> : variant == 1 ? trav::traverse_kernel<MODE, false, 1>
-                                                                                  : trav::traverse_kernel<MODE, false, 0>;
+  const bool hp = MODE == trav::MODE_KNN && k > trav::LIST_MAX_K;
+#define TK_PICK(CNT, VAR) (hp ? trav::traverse_kernel<MODE, CNT, VAR, true> : trav::traverse_kernel<MODE, CNT, VAR, false>)
+  if (c->counters) kern = variant == 2 ? TK_PICK(true, 2) : variant == 1 ? TK_PICK(true, 1) : TK_PICK(true, 0);
+  else kern = variant == 2 ? TK_PICK(false, 2) : variant == 1 ? TK_PICK(false, 1) : TK_PICK(false, 0);
+#undef TK_PICK
   TK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)grid, warps * 32, smem, c->stream>>>(P);
   TK_CUDA(c, cudaGetLastError());
@@ -313,10 +314,19 @@ int run_rounds(tknn_ctx* c, const Job& job, int* launches_io) {
 // Sampled k-th-neighbour distance -> start radius (role of Util/random_sample.py:5-32).
 int estimate_radius(tknn_ctx* c, const float4* queries, uint64_t q_begin, uint64_t nq, const int32_t* self_ids,
                     int self_is_row, int k, float* out, int* launches) {
-  const uint64_t want = std::min<uint64_t>((uint64_t)std::max(1, c->sample_groups) * 32, nq);
+  // sample_groups runs of 32 consecutive sorted positions: the 32 threads of a warp of the thread-per-query
+  // kernel then walk nearly the same nodes and leaves (shared cache lines, similar trip counts)
+  const uint64_t groups = (nq + 31) / 32;
+  const uint64_t sg = std::min<uint64_t>((uint64_t)std::max(1, c->sample_groups), groups);
   std::vector<uint32_t> q;
-  q.reserve(want);
-  for (uint64_t s = 0; s < want; ++s) q.push_back((uint32_t)(q_begin + (nq * s) / want));  // evenly spaced, ascending
+  q.reserve(sg * 32);
+  for (uint64_t s = 0; s < sg; ++s) {
+    const uint64_t g = (groups * s) / sg;
+    for (int l = 0; l < 32; ++l) {
+      const uint64_t pos = g * 32 + l;
+      if (pos < nq) q.push_back((uint32_t)(q_begin + pos));
+    }
+  }
   const size_t m = q.size();
   TK_TRY(ensure(c, c->sample, m * sizeof(uint32_t) + m * (size_t)k * (sizeof(int32_t) + sizeof(float))));
   uint32_t* dq = c->sample.as<uint32_t>();
