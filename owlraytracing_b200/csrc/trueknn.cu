@@ -171,13 +171,27 @@ template <int MODE>
 int launch_traverse(tknn_ctx* c, const trav::Params& P) {
   const int k = MODE == trav::MODE_KNN ? P.k : 0;
   const size_t per_warp = trav::smem_per_warp(k);
-  // block shape: the warps-per-block that keeps the most warps resident per SM (227 KB shared, 64 warps)
+  // pick the kernel variant first: its register count enters the block-shape choice
+  void (*kern)(const trav::Params) = nullptr;
+  const bool ties = c->tie_pruning == 1 || (c->tie_pruning == 0 && c->has_dup_leaves);
+  const int variant = MODE != trav::MODE_KNN ? 0 : (ties ? 2 : (c->approx_filter ? 1 : 0));
+  const bool hp = MODE == trav::MODE_KNN && k > trav::LIST_MAX_K;
+#define TK_PICK(CNT, VAR) (hp ? trav::traverse_kernel<MODE, CNT, VAR, true> : trav::traverse_kernel<MODE, CNT, VAR, false>)
+  if (c->counters) kern = variant == 2 ? TK_PICK(true, 2) : variant == 1 ? TK_PICK(true, 1) : TK_PICK(true, 0);
+  else kern = variant == 2 ? TK_PICK(false, 2) : variant == 1 ? TK_PICK(false, 1) : TK_PICK(false, 0);
+#undef TK_PICK
+  cudaFuncAttributes fa;
+  TK_CUDA(c, cudaFuncGetAttributes(&fa, kern));
+  const int regs_alloc = ((fa.numRegs + 7) / 8) * 8;  // registers are allocated in units of 8 per thread
+  // block shape: the warps-per-block that keeps the most warps resident per SM
+  // (227 KB shared memory, 64 K registers, 64 warps, 32 blocks)
   const size_t sm_smem = 227 * 1024;
   int warps = 0, bps = 1, best = 0;
   for (int w = 8; w >= 1; --w) {
     const size_t need_b = per_warp * w + 1024;  // + per-block reservation
     if (need_b > sm_smem) continue;
     int b = (int)std::min<size_t>(sm_smem / need_b, (size_t)(64 / w));
+    b = std::min(b, 65536 / (regs_alloc * 32 * w));
     b = std::min(b, 32);
     if (b * w > best) { best = b * w; warps = w; bps = b; }
   }
@@ -187,14 +201,6 @@ int launch_traverse(tknn_ctx* c, const trav::Params& P) {
   uint64_t grid = (uint64_t)c->sm_count * bps;
   const uint64_t need = ((uint64_t)P.n_groups + warps - 1) / warps;
   if (grid > need) grid = std::max<uint64_t>(1, need);
-  void (*kern)(const trav::Params) = nullptr;
-  const bool ties = c->tie_pruning == 1 || (c->tie_pruning == 0 && c->has_dup_leaves);
-  const int variant = MODE != trav::MODE_KNN ? 0 : (ties ? 2 : (c->approx_filter ? 1 : 0));
-  const bool hp = MODE == trav::MODE_KNN && k > trav::LIST_MAX_K;
-#define TK_PICK(CNT, VAR) (hp ? trav::traverse_kernel<MODE, CNT, VAR, true> : trav::traverse_kernel<MODE, CNT, VAR, false>)
-  if (c->counters) kern = variant == 2 ? TK_PICK(true, 2) : variant == 1 ? TK_PICK(true, 1) : TK_PICK(true, 0);
-  else kern = variant == 2 ? TK_PICK(false, 2) : variant == 1 ? TK_PICK(false, 1) : TK_PICK(false, 0);
-#undef TK_PICK
   TK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)grid, warps * 32, smem, c->stream>>>(P);
   TK_CUDA(c, cudaGetLastError());
