@@ -14,9 +14,15 @@ namespace rsort {
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int PASSES = 64 / RADIX_BITS;
-constexpr int THREADS = 256;
+#ifndef TKNN_SORT_THREADS
+#define TKNN_SORT_THREADS 256
+#endif
+#ifndef TKNN_SORT_ITEMS
+#define TKNN_SORT_ITEMS 16
+#endif
+constexpr int THREADS = TKNN_SORT_THREADS;
 constexpr int WARPS = THREADS / 32;
-constexpr int ITEMS = 16;                   // pairs per thread
+constexpr int ITEMS = TKNN_SORT_ITEMS;      // pairs per thread
 constexpr int TILE = THREADS * ITEMS;       // 4096 pairs per tile
 constexpr uint32_t FLAG_AGG = 1u << 30;     // tile aggregate published
 constexpr uint32_t FLAG_PREFIX = 2u << 30;  // inclusive prefix published
