@@ -198,6 +198,36 @@ __device__ __forceinline__ float prefilter_tau(float bound, float qq) {
   return (qq < 1e30f && bound < 1e30f) ? tau : INFINITY;
 }
 
+// ---- packed exact filter (sm_100a FADD2 / FMUL2 / FFMA2) -----------------------------------------
+// The traversal is instruction-issue bound, and Blackwell's packed fp32x2 instructions
+// evaluate the distance chain of TWO points per issue slot with the same IEEE round-to-nearest result
+// per component as the scalar __fsub_rn/__fmul_rn/__fmaf_rn chain of dist2().  The leaf is therefore
+// also staged as three coordinate arrays (sx, sy, sz), so one LDS.128 per axis yields two aligned
+// operand pairs: 4 points cost 3 LDS.128 + 12 packed FP + 4 FSETP/SEL instead of 4 LDS.128 + 24 FP + 8.
+// Lanes past the leaf's last point stage NaN in sx: a NaN distance never satisfies d <= bound, so the
+// padded tail of the last chunk of 4 drops out without a bounds test.
+__device__ __forceinline__ float2 dist2_x2(float2 qx, float2 qy, float2 qz, float2 px, float2 py, float2 pz) {
+  const float2 dx = __fadd2_rn(qx, make_float2(-px.x, -px.y));
+  const float2 dy = __fadd2_rn(qy, make_float2(-py.x, -py.y));
+  const float2 dz = __fadd2_rn(qz, make_float2(-pz.x, -pz.y));
+  return __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+}
+
+// bit i of the result: point j0 + i of the staged leaf is within `bound` of the lane's query
+__device__ __forceinline__ uint32_t filter4(const float* sx, int j0, float2 qx, float2 qy, float2 qz, float bound) {
+  const float4 X = *reinterpret_cast<const float4*>(sx + j0);
+  const float4 Y = *reinterpret_cast<const float4*>(sx + MAX_LEAF + j0);
+  const float4 Z = *reinterpret_cast<const float4*>(sx + 2 * MAX_LEAF + j0);
+  const float2 a = dist2_x2(qx, qy, qz, make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y));
+  const float2 b = dist2_x2(qx, qy, qz, make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w));
+  uint32_t m = 0;
+  if (a.x <= bound) m |= 1u;
+  if (a.y <= bound) m |= 2u;
+  if (b.x <= bound) m |= 4u;
+  if (b.y <= bound) m |= 8u;
+  return m;
+}
+
 // VARIANT: 0 = exact filter, 1 = conservative pre-filter (audited option), 2 = exact filter + index-aware
 // tie pruning (chosen by the host when the build found leaves of coincident points).
 // HEAP: k > LIST_MAX_K (compile-time, so the small-k kernel does not carry the heap code).
@@ -216,6 +246,7 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
   // second staging array (relative coordinates + squared norm) for the pre-filter, behind the k-list
   float4* stage2 = reinterpret_cast<float4*>(wbase + MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int) +
                                              (size_t)(k + 1) * 32 * sizeof(uint64_t));
+  float* soa = reinterpret_cast<float*>(stage2);  // exact filter: the leaf's x[32] | y[32] | z[32] (same region)
 
   unsigned long long c_nodes = 0, c_tests = 0, c_ins = 0, c_wnodes = 0, c_wleaves = 0, c_wpts = 0, c_viol = 0;
 
@@ -287,7 +318,11 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
             if (APPROX && MODE == MODE_KNN) {
               const float rx = __fsub_rn(pl.x, cx), ry = __fsub_rn(pl.y, cy), rz = __fsub_rn(pl.z, cz);
               stage2[lane] = make_float4(rx, ry, rz, __fmaf_rn(rz, rz, __fmaf_rn(ry, ry, __fmul_rn(rx, rx))));
+            } else if (MODE == MODE_KNN) {
+              soa[lane] = pl.x; soa[MAX_LEAF + lane] = pl.y; soa[2 * MAX_LEAF + lane] = pl.z;
             }
+          } else if (!APPROX && MODE == MODE_KNN) {
+            soa[lane] = __int_as_float(0x7fc00000);  // NaN: the padded tail of the last chunk never passes
           }
           __syncwarp();
           if (COUNT) { c_tests += valid ? lcount : 0; c_wleaves += 1; c_wpts += lcount; }
@@ -326,22 +361,14 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
                 }
               }
             } else {
+              const float2 qx2 = make_float2(q.x, q.x), qy2 = make_float2(q.y, q.y), qz2 = make_float2(q.z, q.z);
               for (; j0 + 8 <= lcount; j0 += 8) {
-                uint32_t m8 = 0;
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                  const float4 p = stage[j0 + jj];
-                  const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
-                  if (d <= bound) m8 |= (1u << jj);
-                }
+                const uint32_t m8 = filter4(soa, j0, qx2, qy2, qz2, bound) | (filter4(soa, j0 + 4, qx2, qy2, qz2, bound) << 4);
                 mask |= m8 << j0;
               }
 #pragma unroll 1
-              for (; j0 < lcount; ++j0) {  // not unrolled: code size matters more here than the few tail tests
-                const float4 p = stage[j0];
-                const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
-                if (d <= bound) mask |= (1u << j0);
-              }
+              for (; j0 < lcount; j0 += 4)  // tail in chunks of 4, NaN-padded past the last point
+                mask |= filter4(soa, j0, qx2, qy2, qz2, bound) << j0;
             }
             // insert: only lanes with survivors do work; the bound tightens as they go
             while (__any_sync(FULL_MASK, mask != 0u)) {
