@@ -350,8 +350,9 @@ __global__ void __launch_bounds__(THREADS) karras_kernel(const uint64_t* __restr
 
 // ------------------------------------------------------------------------------------------------
 // Bottom-up refit: one thread per leaf computes the leaf box and climbs; at every internal node the
-// first arriver stores its child's record and stops, the second one merges and continues.
-// A child's 32 B record (box + ref + count) is written with two 16-byte stores.
+// first arriver parks its child's record (box + ref + count, two 16-byte stores) in its half of the node
+// and stops; the second one reads it back, writes the whole node in its final interleaved layout
+// (common.cuh: Node) with four 16-byte stores, merges and continues.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS) refit_kernel(const float4* __restrict__ pts,
                                                         const uint32_t* __restrict__ leaf_start, uint32_t n_leaves,
@@ -388,6 +389,15 @@ __global__ void __launch_bounds__(THREADS) refit_kernel(const float4* __restrict
     const float4* sib = reinterpret_cast<const float4*>(nodes + node) + 2 * (1 - slot);
     const float4 slo = __ldcg(sib), shi = __ldcg(sib + 1);
     mn = min(mn, __ldcg(&node_min_idx[2 * node + (1 - slot)]));
+    {  // both children are known: the node in its final layout (child 0 low, child 1 high in every pair)
+      const float4 mlo = make_float4(lo.x, lo.y, lo.z, __int_as_float(ref)), mhi = make_float4(hi.x, hi.y, hi.z, __int_as_float(cnt));
+      const float4 l0 = slot ? slo : mlo, h0 = slot ? shi : mhi, l1 = slot ? mlo : slo, h1 = slot ? mhi : shi;
+      float4* out = reinterpret_cast<float4*>(nodes + node);
+      __stcg(out, make_float4(l0.x, l1.x, l0.y, l1.y));
+      __stcg(out + 1, make_float4(l0.z, l1.z, h0.x, h1.x));
+      __stcg(out + 2, make_float4(h0.y, h1.y, h0.z, h1.z));
+      __stcg(out + 3, make_float4(l0.w, l1.w, h0.w, h1.w));
+    }
     lo.x = fminf(lo.x, slo.x); lo.y = fminf(lo.y, slo.y); lo.z = fminf(lo.z, slo.z);
     hi.x = fmaxf(hi.x, shi.x); hi.y = fmaxf(hi.y, shi.y); hi.z = fmaxf(hi.z, shi.z);
     if (node == 0) {

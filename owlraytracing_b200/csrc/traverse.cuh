@@ -283,12 +283,12 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
     int node = 0;
     for (;;) {
       const float4* np = reinterpret_cast<const float4*>(P.nodes + node);
-      const float4 lo0 = __ldg(np), hi0 = __ldg(np + 1), lo1 = __ldg(np + 2), hi1 = __ldg(np + 3);
-      const float d0 = box_dist2(q.x, q.y, q.z, lo0, hi0);
-      const float d1 = box_dist2(q.x, q.y, q.z, lo1, hi1);
+      const float4 na = __ldg(np), nb = __ldg(np + 1), nc = __ldg(np + 2), nd = __ldg(np + 3);
+      const float2 d01 = box_dist2_x2(q.x, q.y, q.z, na, nb, nc);
+      const float d0 = d01.x, d1 = d01.y;
       if (COUNT) { c_nodes += valid ? 1 : 0; c_wnodes += 1; }
-      const int ref0 = __float_as_int(lo0.w), cnt0 = __float_as_int(hi0.w);
-      const int ref1 = __float_as_int(lo1.w), cnt1 = __float_as_int(hi1.w);
+      const int ref0 = __float_as_int(nd.x), cnt0 = __float_as_int(nd.z);
+      const int ref1 = __float_as_int(nd.y), cnt1 = __float_as_int(nd.w);
 
       // ---- leaf children first (they tighten the bounds before anything is pushed) ----
       if ((cnt0 | cnt1) != 0) {
@@ -497,12 +497,12 @@ __global__ void __launch_bounds__(SPARSE_THREADS) traverse_sparse_kernel(const P
     int node = 0;
     for (;;) {
       const float4* np = reinterpret_cast<const float4*>(P.nodes + node);
-      const float4 lo0 = __ldg(np), hi0 = __ldg(np + 1), lo1 = __ldg(np + 2), hi1 = __ldg(np + 3);
-      const float d0 = box_dist2(q.x, q.y, q.z, lo0, hi0);
-      const float d1 = box_dist2(q.x, q.y, q.z, lo1, hi1);
+      const float4 na = __ldg(np), nb = __ldg(np + 1), nc = __ldg(np + 2), nd = __ldg(np + 3);
+      const float2 d01 = box_dist2_x2(q.x, q.y, q.z, na, nb, nc);
+      const float d0 = d01.x, d1 = d01.y;
       if (COUNT) c_nodes += 1;
-      const int ref0 = __float_as_int(lo0.w), cnt0 = __float_as_int(hi0.w);
-      const int ref1 = __float_as_int(lo1.w), cnt1 = __float_as_int(hi1.w);
+      const int ref0 = __float_as_int(nd.x), cnt0 = __float_as_int(nd.z);
+      const int ref1 = __float_as_int(nd.y), cnt1 = __float_as_int(nd.w);
       const bool swap = d1 < d0;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {

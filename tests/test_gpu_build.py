@@ -47,10 +47,11 @@ def _walk(nodes, pts, leaf_start):
     starts = set(leaf_start[:-1].tolist())
 
     def box_of_child(node, slot):
-        lo = nodes[node, 8 * slot: 8 * slot + 3]
-        hi = nodes[node, 8 * slot + 4: 8 * slot + 7]
-        ref = int(refs[node, 8 * slot + 3])
-        cnt = int(refs[node, 8 * slot + 7])
+        # interleaved layout (common.cuh: Node): every pair of words is (child 0, child 1)
+        lo = nodes[node, [0 + slot, 2 + slot, 4 + slot]]
+        hi = nodes[node, [6 + slot, 8 + slot, 10 + slot]]
+        ref = int(refs[node, 12 + slot])
+        cnt = int(refs[node, 14 + slot])
         if cnt > 0:
             assert ref in starts
             p = pts[ref: ref + cnt, :3]
