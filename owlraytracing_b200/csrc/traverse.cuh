@@ -90,6 +90,30 @@ __device__ __forceinline__ void heap_sift_root(uint64_t* H, int size, uint64_t k
   H[i * 32] = key;
 }
 
+// Same, for a heap whose slots [size, size + 3] hold 0 (<= every key): the four child loads need no bounds
+// tests, and the maximum is found by a two-level tournament (two independent compares, then one) instead
+// of a chain of three.  33 instead of 48 SASS instructions per level; used by the cooperative kernel,
+// which pads its heaps (klist_slots) and zeroes the slots it vacates at emit time.
+__device__ __forceinline__ void heap_sift_root_padded(uint64_t* A, int size, uint64_t key) {
+  int i = 0;
+  for (;;) {
+    const int c = 4 * i + 1;
+    if (c >= size) break;
+    const uint64_t* p = A + c * 32;
+    const uint64_t k0 = p[0], k1 = p[32], k2 = p[64], k3 = p[96];
+    const bool b01 = k1 > k0, b23 = k3 > k2;
+    const uint64_t m01 = b01 ? k1 : k0, m23 = b23 ? k3 : k2;
+    const int i01 = b01 ? c + 1 : c, i23 = b23 ? c + 3 : c + 2;  // selected with the values: the predicates die here
+    const bool b = m23 > m01;
+    const uint64_t mk = b ? m23 : m01;
+    const int im = b ? i23 : i01;
+    if (mk <= key) break;
+    A[i * 32] = mk;
+    i = im;
+  }
+  A[i * 32] = key;
+}
+
 // ---- bounded ASCENDING list of u64 keys in shared memory (slot s of lane l at L[s * 32 + l]) ----
 // Candidates arrive roughly nearest-first, so a new key usually lands near the tail: the backward
 // shift is short, and the list needs no heap-sort at emit time.  Precondition: cnt < k or key < L[k-1].
@@ -122,25 +146,38 @@ constexpr int LIST_MAX_K = 24;
 // H = sentinel slot of the lane's region; the heap (large k) uses slots 1..k as its 0-based array
 __device__ __forceinline__ uint64_t kl_worst(const uint64_t* H, int k, bool heap) { return heap ? H[32] : H[k * 32]; }
 
+// PADDED: the heap's slots past its last entry hold 0 (cooperative kernel; see heap_sift_root_padded)
+template <bool PADDED = false>
 __device__ __forceinline__ void kl_insert(uint64_t* H, int& cnt, int k, uint64_t key, bool heap) {
   if (heap) {
     if (cnt < k) heap_push(H + 32, cnt, key);
+    else if (PADDED) heap_sift_root_padded(H + 32, k, key);
     else heap_sift_root(H + 32, k, key);
   } else {
     list_insert(H, cnt, k, key);
   }
 }
 
-// writes the k-list ascending to (io, dd); destroys the heap
+// writes the k-list ascending to (io, dd); destroys the heap (PADDED: leaves it all zero)
+template <bool PADDED = false>
 __device__ __forceinline__ void kl_emit(uint64_t* H, int cnt, int k, bool heap, bool squared, int32_t* io, float* dd) {
   for (int i = k - 1; i >= cnt; --i) { io[i] = -1; dd[i] = FLT_MAX; }
   if (heap) {
     uint64_t* A = H + 32;
+    if (PADDED && cnt < k) {  // a short heap (capped final round): slots past it may hold an earlier group's keys
+      A[cnt * 32] = 0; A[(cnt + 1) * 32] = 0; A[(cnt + 2) * 32] = 0;
+    }
     for (int i = cnt - 1; i >= 0; --i) {
       const uint64_t top = A[0];
       io[i] = key_idx(top);
       dd[i] = squared ? key_d2(top) : __fsqrt_rn(key_d2(top));
-      if (i > 0) heap_sift_root(A, i, A[i * 32]);
+      if (PADDED) {
+        const uint64_t last = A[i * 32];
+        A[i * 32] = 0;  // the vacated slot joins the zero padding
+        if (i > 0) heap_sift_root_padded(A, i, last);
+      } else if (i > 0) {
+        heap_sift_root(A, i, A[i * 32]);
+      }
     }
   } else {
     for (int i = 0; i < cnt; ++i) {
@@ -151,8 +188,11 @@ __device__ __forceinline__ void kl_emit(uint64_t* H, int cnt, int k, bool heap, 
   }
 }
 
+// k-list slots per lane in the cooperative kernel: sentinel + k entries, + 3 zero slots behind a heap
+__host__ __device__ inline int klist_slots(int k) { return k > LIST_MAX_K ? k + 4 : k + 1; }
+
 __host__ __device__ inline size_t smem_per_warp(int k) {
-  return (size_t)(k + 1) * 32 * sizeof(uint64_t) + 2 * MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int);
+  return (size_t)klist_slots(k) * 32 * sizeof(uint64_t) + 2 * MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int);
 }
 
 // ---- index-aware pruning of exact ties ----------------------------------------------------------
@@ -245,10 +285,13 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
   uint64_t* H = reinterpret_cast<uint64_t*>(wbase + MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int)) + lane;
   // second staging array (relative coordinates + squared norm) for the pre-filter, behind the k-list
   float4* stage2 = reinterpret_cast<float4*>(wbase + MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int) +
-                                             (size_t)(k + 1) * 32 * sizeof(uint64_t));
+                                             (size_t)klist_slots(k) * 32 * sizeof(uint64_t));
   float* soa = reinterpret_cast<float*>(stage2);  // exact filter: the leaf's x[32] | y[32] | z[32] (same region)
 
   unsigned long long c_nodes = 0, c_tests = 0, c_ins = 0, c_wnodes = 0, c_wleaves = 0, c_wpts = 0, c_viol = 0;
+  if (HEAP && MODE == MODE_KNN) {  // zero padding behind the heap (never written again)
+    H[(k + 1) * 32] = 0; H[(k + 2) * 32] = 0; H[(k + 3) * 32] = 0;
+  }
 
   for (;;) {
     uint32_t group = 0;
@@ -381,7 +424,7 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
                 if (pid != self && d <= bound) {
                   const uint64_t key = make_key(d, pid);
                   if (cnt < k || key < kl_worst(H, k, heap)) {
-                    kl_insert(H, cnt, k, key, heap);
+                    kl_insert<true>(H, cnt, k, key, heap);
                     if (cnt == k) bound = key_d2(kl_worst(H, k, heap));
                     if (COUNT) c_ins += 1;
                   }
@@ -436,7 +479,7 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
         int32_t* io = P.idx_out + row * (uint64_t)k;
         float* dd = P.dist_out + row * (uint64_t)k;
         if (P.row_mode && P.qid_out) P.qid_out[row] = row_id;
-        kl_emit(H, cnt, k, heap, P.squared != 0, io, dd);
+        kl_emit<true>(H, cnt, k, heap, P.squared != 0, io, dd);
       }
     }
     __syncwarp();
