@@ -191,7 +191,21 @@ int launch_traverse(tknn_ctx* c, const trav::Params& P) {
     const size_t need_b = per_warp * w + 1024;  // + per-block reservation
     if (need_b > sm_smem) continue;
     int b = (int)std::min<size_t>(sm_smem / need_b, (size_t)(64 / w));
-    b = std::min(b, 65536 / (regs_alloc * 32 * w));
+    // registers: each of the 4 SM sub-partitions owns 16 K of them and the warps of successive blocks go to
+    // the sub-partitions round-robin, so a block fits only while no sub-partition overflows (ncu: at 48
+    // registers 224-thread blocks were limited to 5 per SM and 192-thread blocks to 6, not 6 and 7)
+    {
+      const int per_smsp = 16384 / (regs_alloc * 32);
+      int load[4] = {0, 0, 0, 0}, next = 0, fit = 0;
+      for (; fit < b; ++fit) {
+        int trial[4] = {load[0], load[1], load[2], load[3]};
+        for (int i = 0; i < w; ++i) ++trial[(next + i) & 3];
+        if (std::max(std::max(trial[0], trial[1]), std::max(trial[2], trial[3])) > per_smsp) break;
+        for (int i = 0; i < 4; ++i) load[i] = trial[i];
+        next = (next + w) & 3;
+      }
+      b = fit;
+    }
     b = std::min(b, 32);
     if (b * w > best) { best = b * w; warps = w; bps = b; }
   }
