@@ -72,6 +72,20 @@ __global__ void __launch_bounds__(RADIX) scan_histogram_kernel(uint32_t* __restr
   h[threadIdx.x] = off + inc - v;
 }
 
+// Lanes holding the same 8-bit digit.  Eight ballots (one per digit bit) instead of `match.any`: the
+// instruction loops over the distinct values in the warp (~30 of them for 8-bit digits) and its latency
+// sat on the ranking loop's critical path — 38 % of the pass's stall samples (profiles/r1_sort_v8_*).
+__device__ __forceinline__ uint32_t match_digit(uint32_t d) {
+  uint32_t peers = FULL_MASK;
+#pragma unroll
+  for (int b = 0; b < RADIX_BITS; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const uint32_t m = __ballot_sync(FULL_MASK, bit);
+    peers &= bit ? m : ~m;
+  }
+  return peers;
+}
+
 // One onesweep pass over digit `shift / 8`.
 __global__ void __launch_bounds__(THREADS)
     onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
@@ -106,12 +120,12 @@ __global__ void __launch_bounds__(THREADS)
     key[i] = ok ? keys_in[idx] : ~0ull;  // padding ranks after every real key of digit 255
     val[i] = ok ? vals_in[idx] : 0u;
   }
-  // warp-local stable ranking: lanes holding the same digit find each other with match.any; the
+  // warp-local stable ranking: lanes holding the same digit find each other (match_digit); the
   // lowest of them bumps the warp's digit counter for the whole peer group.
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     const uint32_t d = (uint32_t)(key[i] >> shift) & (RADIX - 1);
-    const uint32_t peers = __match_any_sync(FULL_MASK, d);
+    const uint32_t peers = match_digit(d);
     const int leader = __ffs(peers) - 1;
     uint32_t old = 0;
     if (lane == leader) {
