@@ -28,6 +28,7 @@ constexpr uint32_t FLAG_AGG = 1u << 30;     // tile aggregate published
 constexpr uint32_t FLAG_PREFIX = 2u << 30;  // inclusive prefix published
 constexpr uint32_t FLAG_MASK = 3u << 30;
 constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
+constexpr int LOOKBACK = 8;                   // predecessors fetched per look-back step
 constexpr uint64_t MAX_N = (1ull << 30) - 1;  // counts share a word with the two flag bits
 
 constexpr size_t DYN_SMEM = (size_t)TILE * (sizeof(uint64_t) + sizeof(uint32_t));
@@ -54,8 +55,11 @@ __global__ void __launch_bounds__(THREADS) histogram_kernel(const uint64_t* __re
 }
 
 // in-place exclusive scan of each pass's 256 bins: one block per pass.
-__global__ void __launch_bounds__(RADIX) scan_histogram_kernel(uint32_t* __restrict__ hist) {
+// Block 0 also writes the LOOKBACK "prefix 0" rows that sit in front of the tile status array.
+__global__ void __launch_bounds__(RADIX) scan_histogram_kernel(uint32_t* __restrict__ hist, uint32_t* __restrict__ status_pad) {
   __shared__ uint32_t s_warp[RADIX / 32];
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < LOOKBACK * RADIX; i += RADIX) status_pad[i] = FLAG_PREFIX;
   uint32_t* h = hist + blockIdx.x * RADIX;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t v = h[threadIdx.x];
@@ -87,7 +91,7 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d) {
 }
 
 // One onesweep pass over digit `shift / 8`.
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 3)
     onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                     uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint64_t n, int shift,
                     const uint32_t* __restrict__ bin_offset, uint32_t* status, uint32_t* tile_counter) {
@@ -165,16 +169,32 @@ __global__ void __launch_bounds__(THREADS)
   s_digit_start[d] = dstart;
 
   // decoupled look-back over the preceding tiles for digit d
+  // The walk is latency bound (one dependent global load per predecessor: 30 % of the pass's stall samples),
+  // so LOOKBACK predecessors are fetched at once and consumed in order; a predecessor that has published
+  // nothing yet restarts the window at that tile.
   uint32_t excl = 0;
   if (tile > 0) {
     int64_t t = (int64_t)tile - 1;
-    for (;;) {
-      const volatile uint32_t* p = status + (size_t)t * RADIX + d;
-      uint32_t v;
-      do { v = *p; } while ((v & FLAG_MASK) == 0);
-      excl += v & VALUE_MASK;
-      if (v & FLAG_PREFIX) break;
-      --t;
+    bool done = false;
+    while (!done) {
+      uint32_t v[LOOKBACK];
+      // rows -1 .. -LOOKBACK in front of tile 0 hold "prefix 0" (scan_histogram_kernel), so the window needs
+      // no range test: the walk itself always ends at tile 0, which publishes FLAG_PREFIX directly
+      const volatile uint32_t* p = status + t * RADIX + d;
+#pragma unroll
+      for (int w = 0; w < LOOKBACK; ++w) v[w] = *(p - w * RADIX);
+      int used = 0;
+#pragma unroll
+      for (int w = 0; w < LOOKBACK; ++w) {
+        if (!done && used == w) {
+          if ((v[w] & FLAG_MASK) != 0) {
+            excl += v[w] & VALUE_MASK;
+            ++used;
+            if (v[w] & FLAG_PREFIX) done = true;
+          }
+        }
+      }
+      t -= used;  // used < LOOKBACK: tile t - used was not ready — poll again from there
     }
     atomicExch(&st[d], ((excl + total) & VALUE_MASK) | FLAG_PREFIX);
   }
@@ -200,8 +220,9 @@ __global__ void __launch_bounds__(THREADS)
   }
 }
 
-// temp layout (uint32 words): hist[PASSES*RADIX] | counters[PASSES] (+pad to 16) | status[tiles*RADIX]
-inline size_t temp_words(uint64_t n) { return (size_t)PASSES * RADIX + 16 + (size_t)num_tiles(n) * RADIX; }
+// temp layout (uint32 words): hist[PASSES*RADIX] | counters[PASSES] (+pad to 16) | LOOKBACK rows of "prefix 0" |
+// status[tiles*RADIX]
+inline size_t temp_words(uint64_t n) { return (size_t)PASSES * RADIX + 16 + (size_t)(LOOKBACK + num_tiles(n)) * RADIX; }
 
 // Sorts (keys_a, vals_a) on the low 8 * passes key bits (keys must be zero above them) using
 // (keys_b, vals_b) as the alternate buffer.  The result ends in the `a` buffers when `passes` is even
@@ -214,7 +235,8 @@ inline int sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint
   if (passes > PASSES) passes = PASSES;
   uint32_t* hist = temp;
   uint32_t* counters = temp + PASSES * RADIX;
-  uint32_t* status = counters + 16;
+  uint32_t* status_pad = counters + 16;
+  uint32_t* status = status_pad + LOOKBACK * RADIX;
   const uint32_t tiles = num_tiles(n);
   cudaMemsetAsync(temp, 0, sizeof(uint32_t) * (PASSES * RADIX + 16), stream);
   cudaFuncSetAttribute(onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM);
@@ -222,7 +244,7 @@ inline int sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint
   const uint64_t hmax = (uint64_t)sm_count * 8;
   if (hb > hmax) hb = hmax;
   histogram_kernel<<<(unsigned)hb, THREADS, 0, stream>>>(keys_a, n, hist);
-  scan_histogram_kernel<<<PASSES, RADIX, 0, stream>>>(hist);
+  scan_histogram_kernel<<<PASSES, RADIX, 0, stream>>>(hist, status_pad);
   int launches = 2;
   uint64_t *kin = keys_a, *kout = keys_b;
   uint32_t *vin = vals_a, *vout = vals_b;
