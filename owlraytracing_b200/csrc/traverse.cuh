@@ -361,20 +361,20 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
             if (APPROX && MODE == MODE_KNN) {
               const float rx = __fsub_rn(pl.x, cx), ry = __fsub_rn(pl.y, cy), rz = __fsub_rn(pl.z, cz);
               stage2[lane] = make_float4(rx, ry, rz, __fmaf_rn(rz, rz, __fmaf_rn(ry, ry, __fmul_rn(rx, rx))));
-            } else if (MODE == MODE_KNN) {
+            } else {
               soa[lane] = pl.x; soa[MAX_LEAF + lane] = pl.y; soa[2 * MAX_LEAF + lane] = pl.z;
             }
-          } else if (!APPROX && MODE == MODE_KNN) {
+          } else if (!(APPROX && MODE == MODE_KNN)) {
             soa[lane] = __int_as_float(0x7fc00000);  // NaN: the padded tail of the last chunk never passes
           }
           __syncwarp();
           if (COUNT) { c_tests += valid ? lcount : 0; c_wleaves += 1; c_wpts += lcount; }
           if (MODE == MODE_RANGE_COUNT) {
-            for (int j = 0; j < lcount; ++j) {
-              const float4 p = stage[j];
-              const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
-              cnt += (d <= bound && __float_as_int(p.w) != self) ? 1 : 0;
-            }
+            // every point within the radius, the query's own point included: it lies at distance 0 in the one
+            // leaf that holds it and is taken off again at emit time
+            const float2 qx2 = make_float2(q.x, q.x), qy2 = make_float2(q.y, q.y), qz2 = make_float2(q.z, q.z);
+#pragma unroll 1
+            for (int j0 = 0; j0 < lcount; j0 += 4) cnt += __popc(filter4(soa, j0, qx2, qy2, qz2, bound));
           } else {
             // filter: full chunks of 8 with compile-time bit positions, then the remainder one by one
             uint32_t mask = 0;
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
 
     // ---- emit ----
     if (MODE == MODE_RANGE_COUNT) {
-      if (valid) P.count_out[row_id] = (uint32_t)cnt;
+      if (valid) P.count_out[row_id] = (uint32_t)(cnt - (self >= 0 ? 1 : 0));
     } else {
       const bool resolved = valid && cnt == k;
       const bool emit = valid && (resolved || P.final_round);

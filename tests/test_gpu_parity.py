@@ -182,10 +182,19 @@ def test_separate_query_set(knn, oracle):
         assert (idx[i] == ri[0]).all() and (dist[i] == rd[0]).all()
 
 
-def test_range_count(knn, oracle):
-    x = datasets.uniform(8_000, seed=12)
+@pytest.mark.parametrize("cloud", ["uniform", "duplicates", "lidar"])
+def test_range_count(knn, oracle, cloud):
+    """Fixed-radius neighbour counts (DBSCAN core test): self excluded by index, coincident duplicates counted."""
+    if cloud == "uniform":
+        x = datasets.uniform(8_000, seed=12)
+    elif cloud == "duplicates":
+        base = datasets.uniform(6_000, seed=13)
+        x = np.ascontiguousarray(np.concatenate([base, base[:1500], base[:300]], 0))
+    else:
+        x = datasets.lidar_like(9_000, seed=4)
     knn.build(x)
-    for r in (0.0, 0.01, 0.05, 0.2):
+    scale = 1.0 if cloud != "lidar" else 40.0
+    for r in (0.0, 0.01 * scale, 0.05 * scale, 0.2 * scale):
         got = knn.range_count(r)
         assert (np.asarray(got).astype(np.uint32) == oracle.range_count(x, r)).all(), r
 
