@@ -113,27 +113,16 @@ __global__ void __launch_bounds__(THREADS) gather_points_kernel(const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// delta[b] = length of the common prefix of the augmented keys (code, position) at sorted positions
-// b-1 and b (Karras 2012); smaller = stronger split.  delta[0] = 0.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) delta_kernel(const uint64_t* __restrict__ keys, uint64_t n,
-                                                        uint8_t* __restrict__ delta) {
-  const uint64_t b = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
-  if (b >= n) return;
-  if (b == 0) { delta[0] = 0; return; }
-  const uint64_t x = keys[b - 1] ^ keys[b];
-  delta[b] = (uint8_t)(x ? __clzll((long long)x) : 64 + __clz((uint32_t)(b - 1) ^ (uint32_t)b));
-}
-
-// ------------------------------------------------------------------------------------------------
 // Leaf cut.  Policy 0 (default): the leaves are the maximal subtrees of the point-level radix tree
 // holding <= leaf_max points ("treelet collapse"), found WITHOUT building that tree: the internal
 // node that splits at boundary b spans the points between the nearest strictly stronger boundaries
 // on each side, and b is a leaf boundary iff that span exceeds leaf_max — a +-leaf_max window scan.
 // Policy 1: fixed chunks of leaf_max consecutive points.
+// delta[b] = length of the common prefix of the augmented keys (code, position) at sorted positions b-1 and b
+// (Karras 2012); smaller = stronger split; delta[0] = 0.  It is computed from the keys while staging.
 // Output: one ballot word per 32 boundaries.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) leaf_flag_kernel(const uint8_t* __restrict__ delta, uint64_t n, int leaf_max,
+__global__ void __launch_bounds__(THREADS) leaf_flag_kernel(const uint64_t* __restrict__ keys, uint64_t n, int leaf_max,
                                                             int policy, uint64_t force_split,
                                                             uint32_t* __restrict__ ballots) {
   // The block's boundaries plus a halo of MAX_LEAF on both sides, staged once in shared memory.  Positions
@@ -144,7 +133,12 @@ __global__ void __launch_bounds__(THREADS) leaf_flag_kernel(const uint8_t* __res
   const int64_t in = (int64_t)n;
   for (int i = threadIdx.x; i < THREADS + 2 * MAX_LEAF; i += THREADS) {
     const int64_t g = block0 - MAX_LEAF + i;
-    s_delta[i] = (g >= 0 && g < in) ? delta[g] : 0;
+    uint8_t dv = 0;
+    if (g > 0 && g < in) {
+      const uint64_t x = __ldg(&keys[g - 1]) ^ __ldg(&keys[g]);
+      dv = (uint8_t)(x ? __clzll((long long)x) : 64 + __clz((uint32_t)(g - 1) ^ (uint32_t)g));
+    }
+    s_delta[i] = dv;
   }
   __syncthreads();
   const int64_t ib = block0 + threadIdx.x;

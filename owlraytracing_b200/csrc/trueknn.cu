@@ -767,7 +767,6 @@ int tknn_build(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int stride_fl
     if (rc0 == TKNN_OK) rc0 = ensure(c, vals_a, n * sizeof(uint32_t));
     if (rc0 == TKNN_OK) rc0 = ensure(c, vals_b, n * sizeof(uint32_t));
     if (rc0 == TKNN_OK) rc0 = ensure(c, sort_tmp, rsort::temp_words(n) * sizeof(uint32_t));
-    if (rc0 == TKNN_OK) rc0 = ensure(c, delta, n);
     if (rc0 == TKNN_OK) rc0 = ensure(c, ballots, nw0 * sizeof(uint32_t));
     if (rc0 == TKNN_OK) rc0 = ensure(c, c->offsets, (nw0 + 1) * sizeof(uint32_t));
     if (rc0 == TKNN_OK) rc0 = ensure(c, c->block_sums, sizeof(uint32_t) * (size_t)(nw0 / lbvh::SCAN_CHUNK + 2));
@@ -823,14 +822,12 @@ int tknn_build(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int stride_fl
 
   // ---- leaf cut + point gather ----
   const uint64_t nw = (n + 31) / 32;
-  TK_B(ensure(c, delta, n));
   TK_B(ensure(c, ballots, nw * sizeof(uint32_t)));
   TK_B(ensure(c, c->offsets, (nw + 1) * sizeof(uint32_t)));
-  lbvh::delta_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(skeys, n, delta.as<uint8_t>());
   const uint64_t force_split = (n <= (uint64_t)c->leaf_size) ? n / 2 : 0;
   lbvh::leaf_flag_kernel<<<blocks_for(nw * 32, lbvh::THREADS), lbvh::THREADS, 0, st>>>(
-      delta.as<uint8_t>(), n, c->leaf_size, c->leaf_policy, force_split, ballots.as<uint32_t>());
-  launches += 2;
+      skeys, n, c->leaf_size, c->leaf_policy, force_split, ballots.as<uint32_t>());
+  launches += 1;
   TK_B(popc_scan(c, ballots.as<uint32_t>(), nw, c->offsets.as<uint32_t>(), &launches));
   uint32_t m = 0;
   uint32_t bad[1] = {0};
