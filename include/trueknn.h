@@ -72,6 +72,8 @@ enum {
   ,TKNN_OPT_MORTON_BITS = 13   /* Morton bits per axis for the next build: 0 = auto (ceil(log2 n / 3) + 8), else 4..21 */
   ,TKNN_OPT_TIE_PRUNING = 14   /* index-aware pruning of exact distance ties: 0 = auto (kernel variant used when the
                                   build found leaves of coincident points), 1 = always, 2 = never           */
+  ,TKNN_OPT_WARP_ROUND_MAX = 15 /* rounds with at most this many active queries (the start-radius sample, late rounds of a
+                                  few stragglers, small query sets) run one WARP per query (default 49152; 0 = never) */
   ,TKNN_OPT_SPARSE_DIVISOR = 9 /* rounds >= 2 with fewer than n/divisor active queries run the
                                   thread-per-query kernel (default 8; 0 = never)                  */
 };

@@ -623,6 +623,167 @@ __global__ void __launch_bounds__(SPARSE_THREADS) traverse_sparse_kernel(const P
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tiny rounds: one WARP per query.  A thread-per-query walk is a chain of ~100 dependent global loads plus
+// ~670 serial distance tests and takes ~0.3 ms however few queries there are (the start-radius sample of
+// 4 096 queries, a third round of a few hundred stragglers).  Here the 32 lanes test the <= 32 points of a
+// leaf at once (one coalesced load, one ballot) and keep the k-list as one ascending array in shared
+// memory that they shift cooperatively, so the chain shrinks to the node and leaf round trips.  Node
+// decisions are scalar (one query), same strict pruning, same (d2, index) keys => same results.
+// Unresolved queries set their bit in P.unresolved with atomicOr: the host zeroes the words first.
+// ------------------------------------------------------------------------------------------------
+constexpr int WQ_WARPS = 4;  // queries per block
+
+__host__ __device__ inline size_t warpq_smem(int k) {
+  return (size_t)WQ_WARPS * ((size_t)k * sizeof(uint64_t) + STACK_DEPTH * sizeof(int));
+}
+
+// inserts `key` into the ascending list L[0, cnt) of capacity k (the largest entry falls off a full list);
+// precondition: cnt < k or key < L[k - 1]; keys are distinct.  All 32 lanes call it together.
+__device__ __forceinline__ void warp_list_insert(uint64_t* L, int& cnt, int k, uint64_t key, int lane) {
+  int pos = 0;  // entries smaller than key
+  for (int c0 = 0; c0 < cnt; c0 += 32) {
+    const int i = c0 + lane;
+    const uint64_t e = i < cnt ? L[i] : ~0ull;
+    pos += __popc(__ballot_sync(FULL_MASK, e < key));
+  }
+  const int n_new = cnt < k ? cnt + 1 : k;
+  // shift [pos, n_new - 1) one slot up, 32 entries at a time from the top: a chunk reads its old values
+  // (and the last entry of the still untouched chunk below) before it writes
+  for (int c0 = ((n_new - 1) >> 5) << 5; c0 >= ((pos >> 5) << 5); c0 -= 32) {
+    const int i = c0 + lane;
+    const bool moved = i > pos && i < n_new;
+    uint64_t prev = 0;
+    if (moved) prev = L[i - 1];
+    __syncwarp();
+    if (moved) L[i] = prev;
+    else if (i == pos) L[i] = key;
+    __syncwarp();
+  }
+  cnt = n_new;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(WQ_WARPS * 32) traverse_warp_kernel(const Params P) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = P.k;
+  uint64_t* L = reinterpret_cast<uint64_t*>(smem) + (size_t)warp * k;
+  int* stack = reinterpret_cast<int*>(smem + (size_t)WQ_WARPS * k * sizeof(uint64_t)) + warp * STACK_DEPTH;
+  const uint64_t gi = (uint64_t)blockIdx.x * WQ_WARPS + warp;
+  if (gi >= P.n_active) return;  // the whole warp leaves; the kernel has no block-wide barrier
+  const uint64_t qpos = P.queue ? (uint64_t)P.queue[gi] : P.q_begin + gi;
+  const float4 q = __ldg(&P.queries[qpos]);
+  const int row_id = __float_as_int(q.w);
+  const int self = P.self_ids ? P.self_ids[qpos] : (P.self_is_row ? row_id : -1);
+  float bound = P.r2;
+  if (P.query_r2) bound = fminf(bound, P.query_r2[qpos]);
+  int cnt = 0;
+  uint64_t worst = ~0ull;  // L[k - 1] once the list is full
+  unsigned long long c_nodes = 0, c_tests = 0, c_ins = 0;
+
+  int sp = 0;
+  int node = 0;
+  for (;;) {
+    const float4* np = reinterpret_cast<const float4*>(P.nodes + node);
+    const float4 na = __ldg(np), nb = __ldg(np + 1), nc = __ldg(np + 2), nd = __ldg(np + 3);
+    const float2 d01 = box_dist2_x2(q.x, q.y, q.z, na, nb, nc);
+    const float d0 = d01.x, d1 = d01.y;
+    if (COUNT) c_nodes += 1;
+    const int ref0 = __float_as_int(nd.x), cnt0 = __float_as_int(nd.z);
+    const int ref1 = __float_as_int(nd.y), cnt1 = __float_as_int(nd.w);
+    const bool swap = d1 < d0;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      const bool second = (c == 1) != swap;
+      const int lcount = second ? cnt1 : cnt0;
+      if (lcount <= 0) continue;
+      const float dcs = second ? d1 : d0;
+      if (!(dcs <= bound)) continue;
+      if (dcs == bound && cnt == k) {  // exact tie: only a lower index can still win
+        const int2 mi = __ldg(&P.node_min_idx[node]);
+        if ((second ? mi.y : mi.x) >= key_idx(worst)) continue;
+      }
+      if (COUNT) c_tests += lcount;
+      bool pass = false;
+      uint64_t key = 0;
+      if (lane < lcount) {
+        const float4 p = __ldg(&P.pts[(uint64_t)(uint32_t)(second ? ref1 : ref0) + lane]);
+        const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+        const int pid = __float_as_int(p.w);
+        pass = d <= bound && pid != self;
+        key = make_key(d, pid);
+      }
+      unsigned m = __ballot_sync(FULL_MASK, pass);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1u;
+        const uint64_t kk = __shfl_sync(FULL_MASK, key, src);
+        if (cnt == k && kk >= worst) continue;
+        warp_list_insert(L, cnt, k, kk, lane);
+        if (COUNT) c_ins += 1;
+        if (cnt == k) {
+          worst = L[k - 1];
+          bound = key_d2(worst);
+        }
+      }
+    }
+    bool w0 = (cnt0 == 0) && (d0 <= bound);
+    bool w1 = (cnt1 == 0) && (d1 <= bound);
+    if (cnt == k && ((w0 && d0 == bound) || (w1 && d1 == bound))) {
+      const int2 mi = __ldg(&P.node_min_idx[node]);
+      const int wi = key_idx(worst);
+      if (w0 && d0 == bound && mi.x >= wi) w0 = false;
+      if (w1 && d1 == bound && mi.y >= wi) w1 = false;
+    }
+    if (w0 && w1) {
+      if (sp < STACK_DEPTH) {
+        if (lane == 0) stack[sp] = swap ? ref0 : ref1;
+        ++sp;
+      } else if (lane == 0) {
+        atomicOr(P.error, 1u);
+      }
+      node = swap ? ref1 : ref0;
+    } else if (w0) {
+      node = ref0;
+    } else if (w1) {
+      node = ref1;
+    } else {
+      if (sp == 0) break;
+      --sp;
+      __syncwarp();
+      node = stack[sp];
+    }
+  }
+
+  const bool resolved = cnt == k;
+  if (!resolved && P.unresolved && lane == 0) atomicOr(&P.unresolved[gi >> 5], 1u << (unsigned)(gi & 31));
+  if (resolved || P.final_round) {
+    const uint64_t row = P.row_mode == 0 ? (uint64_t)(uint32_t)row_id : (P.row_mode == 1 ? qpos - P.q_begin : gi);
+    int32_t* io = P.idx_out + row * (uint64_t)k;
+    float* dd = P.dist_out + row * (uint64_t)k;
+    if (P.row_mode && P.qid_out && lane == 0) P.qid_out[row] = row_id;
+    __syncwarp();
+    for (int i = lane; i < k; i += 32) {
+      if (i < cnt) {
+        const uint64_t e = L[i];
+        io[i] = key_idx(e);
+        dd[i] = P.squared ? key_d2(e) : __fsqrt_rn(key_d2(e));
+      } else {
+        io[i] = -1;
+        dd[i] = FLT_MAX;
+      }
+    }
+  }
+  if (COUNT && P.counters && lane == 0) {
+    atomicAdd(&P.counters[0], c_nodes);
+    atomicAdd(&P.counters[1], c_tests);
+    atomicAdd(&P.counters[2], c_ins);
+    atomicAdd(&P.counters[3], c_nodes);
+    atomicAdd(&P.counters[5], c_tests);
+  }
+}
+
 // Ballot words of "the point at sorted position p has an original index in [lo, hi)": the first step of
 // cutting the query list into FILE-order slices whose output rows are contiguous (pipelined host output).
 __global__ void __launch_bounds__(256) index_range_flag_kernel(const float4* __restrict__ pts, uint64_t n, uint32_t lo,

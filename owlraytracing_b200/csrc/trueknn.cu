@@ -53,6 +53,7 @@ struct tknn_ctx {
       b_parent_leaf, b_parent_node, b_arrive;
   int keep_scratch = 1;
   int sparse_divisor = 8;
+  int warp_round_max = 49152;  // rounds with at most this many active queries run one warp per query (0 = never)
   int approx_filter = 0;
   int tie_pruning = 0;        // 0 = auto (on when the build saw leaves of coincident points), 1 = on, 2 = off
   int morton_bits = 0;        // 0 = auto (ceil(log2 n / 3) + 8, clamped to [10, 21])
@@ -239,6 +240,25 @@ int launch_traverse_sparse(tknn_ctx* c, const trav::Params& P) {
   return TKNN_OK;
 }
 
+// warp-per-query variant for tiny rounds (the start-radius sample, a handful of stragglers, small query sets)
+int launch_traverse_warp(tknn_ctx* c, const trav::Params& P) {
+  const size_t smem = trav::warpq_smem(P.k);
+  const unsigned grid = (unsigned)((P.n_active + trav::WQ_WARPS - 1) / trav::WQ_WARPS);
+  if (P.unresolved)  // the kernel ORs bits into the ballot words
+    TK_CUDA(c, cudaMemsetAsync(P.unresolved, 0, sizeof(uint32_t) * (size_t)P.n_groups, c->stream));
+  if (c->counters) {
+    auto kern = trav::traverse_warp_kernel<true>;
+    TK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, trav::WQ_WARPS * 32, smem, c->stream>>>(P);
+  } else {
+    auto kern = trav::traverse_warp_kernel<false>;
+    TK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, trav::WQ_WARPS * 32, smem, c->stream>>>(P);
+  }
+  TK_CUDA(c, cudaGetLastError());
+  return TKNN_OK;
+}
+
 int run_rounds(tknn_ctx* c, const Job& job, int* launches_io) {
   uint32_t* sc = c->scalars.as<uint32_t>();
   const uint64_t n0 = job.n_queries;
@@ -298,7 +318,9 @@ int run_rounds(tknn_ctx* c, const Job& job, int* launches_io) {
     const bool sparse = trav::sparse_smem(job.k) <= 200 * 1024 &&
                         (job.force_sparse || (c->sparse_divisor > 0 && queue != nullptr && round > 0 &&
                                               active * (uint64_t)c->sparse_divisor <= n0));
-    if (sparse) TK_TRY(launch_traverse_sparse(c, P));
+    const bool tiny = c->warp_round_max > 0 && active <= (uint64_t)c->warp_round_max;
+    if (tiny) TK_TRY(launch_traverse_warp(c, P));
+    else if (sparse) TK_TRY(launch_traverse_sparse(c, P));
     else TK_TRY(launch_traverse<trav::MODE_KNN>(c, P));
     if (timed) TK_CUDA(c, cudaEventRecord(c->round_ev[4 * round + 3], c->stream));
     ++launches;
@@ -722,6 +744,10 @@ int tknn_set_option(tknn_ctx* c, int key, int64_t value) {
     case TKNN_OPT_SPARSE_DIVISOR:
       if (value < 0 || value > 1000000) return fail(c, TKNN_EINVAL, "sparse divisor outside [0, 1e6]");
       c->sparse_divisor = (int)value;
+      return TKNN_OK;
+    case TKNN_OPT_WARP_ROUND_MAX:
+      if (value < 0 || value > (int64_t)1 << 30) return fail(c, TKNN_EINVAL, "warp round maximum outside [0, 2^30]");
+      c->warp_round_max = (int)value;
       return TKNN_OK;
     case TKNN_OPT_RADIUS_QUANTILE:
       if (value < 0 || value > 1000) return fail(c, TKNN_EINVAL, "radius quantile outside [0, 1000] per mille");

@@ -477,3 +477,50 @@ def test_reach_mask_kernel_is_conservative_and_tight(knn):
     bits_got = ((got[:, None] >> np.arange(w)[None]) & 1).astype(bool)
     assert (bits_got | ~exact).all(), "a reachable rank was missed"
     assert (~bits_got | loose).all(), "a rank out of reach was flagged"
+
+
+def _kernel_choice_clouds():
+    rng = np.random.default_rng(21)
+    base = rng.random((4000, 3), dtype=np.float32)
+    return {
+        "uniform": datasets.uniform(12_000, seed=9),
+        "lidar": datasets.lidar_like(15_000, seed=5),
+        "duplicates": np.ascontiguousarray(np.concatenate([base, base[:2000], np.tile(base[:1], (300, 1))]), np.float32),
+        "lattice": datasets.lattice(12),
+    }
+
+
+@pytest.mark.parametrize("cloud", ["uniform", "lidar", "duplicates", "lattice"])
+@pytest.mark.parametrize("k", [1, 10, 25, 33, 64, 100])
+def test_warp_per_query_kernel_every_round(oracle, cloud, k):
+    """TKNN_OPT_WARP_ROUND_MAX above the cloud size: every round (and the start-radius sample) runs the
+    warp-per-query kernel; a small start radius forces several rounds.  Same exact results."""
+    from owlraytracing_b200 import TrueKNN
+
+    x = _kernel_choice_clouds()[cloud]
+    ref = oracle.knn_kdtree(x, k)
+    with TrueKNN(0, warp_round_max=1 << 30) as t:
+        idx, dist = t.build(x).search(k)
+        assert_knn_equal(idx, dist, *ref, f"warp kernel {cloud} k={k} auto radius")
+        r_small = 0.5 * float(np.median(ref[1][:, 0])) + 1e-6    # most queries miss even their first neighbour
+        idx, dist = t.search(k, r_small)
+        assert_knn_equal(idx, dist, *ref, f"warp kernel {cloud} k={k} small radius")
+        assert t.stats()["rounds"] >= 2
+
+
+@pytest.mark.parametrize("wmax", [0, 49152, 1 << 30])
+def test_round_kernels_agree(oracle, wmax):
+    """The three round kernels (cooperative, thread-per-query, warp-per-query) are interchangeable: the
+    result does not depend on which of them a round ran on."""
+    from owlraytracing_b200 import TrueKNN
+
+    x = datasets.lidar_like(120_000, seed=8)
+    ref = oracle.knn_kdtree(x, 12)
+    with TrueKNN(0, warp_round_max=wmax) as t:
+        idx, dist = t.build(x).search(12, 0.02)                   # many rounds: 0.02 m against a 200 m scene
+        assert_knn_equal(idx, dist, *ref, f"warp_round_max={wmax}")
+        assert t.stats()["rounds"] >= 4
+        if wmax == 0:
+            t.set_option("counters", 1)
+            t.search(12)
+            assert t.stats()["heap_inserts"] >= 12 * x.shape[0]
