@@ -9,8 +9,14 @@
 // within that lane's own bound min(r^2, k-th best d2) (warp vote), so culling is per query, never
 // per group box.  A wanted leaf (<= 32 points, one coalesced 512 B float4 load) is staged in shared
 // memory and broadcast to all lanes: 32 queries x 32 points of distance tests per 512 B fetched.
-// Each lane owns a bounded max-heap of (d2, index) keys; candidates are filtered against the bound
-// into a bit mask first and inserted afterwards, so the divergent part only runs for real hits.
+// Each lane owns a bounded k-list of (d2, index) keys (ascending list for k <= 24, padded 4-ary max-heap
+// above); candidates are filtered against the bound into a bit mask first — two points per issue slot
+// with Blackwell's packed fp32x2 instructions — and inserted afterwards, so the divergent part only
+// runs for real hits.
+//
+// Three kernels share the rules and produce identical results: traverse_kernel (above; dense rounds),
+// traverse_sparse_kernel (one thread per query; rounds whose survivors are spatially incoherent) and
+// traverse_warp_kernel (one warp per query; tiny rounds and the start-radius sample).
 //
 // Exactness: box distances use the same fmaf chain as point distances (monotone under RN), pruning
 // is strict (`>`), ties are resolved on the full (d2, index) key, self is excluded by index.
