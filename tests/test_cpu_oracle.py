@@ -168,6 +168,18 @@ def test_library_exports_every_declared_symbol():
     assert L.tknn_version() == 100
 
 
+def test_option_keys_match_header():
+    """Every TKNN_OPT_* key of the header has the same value in the ctypes mirror and a name in TrueKNN._OPTS."""
+    from owlraytracing_b200.trueknn import TrueKNN
+
+    header = open(os.path.join(ROOT, "include", "trueknn.h")).read()
+    keys = {name: int(val) for name, val in re.findall(r"^\s*,?\s*TKNN_(OPT_\w+)\s*=\s*(\d+)", header, re.M)}
+    assert len(keys) >= 15 and len(set(keys.values())) == len(keys)
+    for name, val in keys.items():
+        assert getattr(_lib, name) == val, name
+    assert sorted(TrueKNN._OPTS.values()) == sorted(keys.values())
+
+
 def test_stats_struct_layout_matches_header():
     src = "#include <stdio.h>\n#include \"trueknn.h\"\nint main(){printf(\"%zu %zu %zu\", sizeof(tknn_stats), " \
           "__builtin_offsetof(tknn_stats, round_ms), __builtin_offsetof(tknn_stats, h2d_bytes));return 0;}"
