@@ -96,29 +96,69 @@ __device__ __forceinline__ void heap_sift_root(uint64_t* H, int size, uint64_t k
   H[i * 32] = key;
 }
 
-// Same, for a heap whose slots [size, size + 3] hold 0 (<= every key): the four child loads need no bounds
-// tests, and the maximum is found by a two-level tournament (two independent compares, then one) instead
-// of a chain of three.  33 instead of 48 SASS instructions per level; used by the cooperative kernel,
-// which pads its heaps (klist_slots) and zeroes the slots it vacates at emit time.
-__device__ __forceinline__ void heap_sift_root_padded(uint64_t* A, int size, uint64_t key) {
+// ---- padded D-ary max-heap of the cooperative kernel ---------------------------------------------
+// Every slot a sift can read past the heap's last entry holds 0 (<= every key), so the D child loads of a
+// level need no bounds tests, and the maximum is found by a tournament (independent compares first) instead
+// of a chain: 32 instead of 48 SASS instructions per level of the 4-ary heap.  heap_pads(k) zero slots follow
+// the k entries; kl_emit zeroes the slots it vacates so the invariant also holds while the heap shrinks.
+// Arity 8 (k = 64 two levels deep: two dependent shared-memory round trips per replacement instead of three)
+// was measured SLOWER on cfg3 (round 1: 55.5 vs 51.0 ms): seven compare-selects per level cost more issue
+// slots than the saved round trip returns.
+#ifndef TKNN_HEAP_ARITY
+#define TKNN_HEAP_ARITY 4
+#endif
+constexpr int PAD_D = TKNN_HEAP_ARITY;  // 4 or 8
+static_assert(PAD_D == 4 || PAD_D == 8, "padded heap arity");
+
+// zero slots needed behind a heap of k entries: the last internal node's children end at PAD_D * ((k - 2) / PAD_D) + PAD_D
+__host__ __device__ inline int heap_pads(int k) { return k >= 2 ? PAD_D * ((k - 2) / PAD_D) + PAD_D - (k - 1) : 1; }
+
+__device__ __forceinline__ void pheap_push(uint64_t* A, int& cnt, uint64_t key) {
+  int i = cnt++;
+  while (i > 0) {
+    const int par = (i - 1) / PAD_D;
+    const uint64_t pk = A[par * 32];
+    if (pk >= key) break;
+    A[i * 32] = pk;
+    i = par;
+  }
+  A[i * 32] = key;
+}
+
+// larger of two (key, slot) pairs, the slot selected with the key so that the predicate dies here
+#define TKNN_MAX2(ka, ia, kb, ib, ko, io)      \
+  const bool b_##ko = (kb) > (ka);               \
+  const uint64_t ko = b_##ko ? (kb) : (ka);      \
+  const int io = b_##ko ? (ib) : (ia);
+
+__device__ __forceinline__ void pheap_sift_root(uint64_t* A, int size, uint64_t key) {
   int i = 0;
   for (;;) {
-    const int c = 4 * i + 1;
+    const int c = PAD_D * i + 1;
     if (c >= size) break;
     const uint64_t* p = A + c * 32;
     const uint64_t k0 = p[0], k1 = p[32], k2 = p[64], k3 = p[96];
-    const bool b01 = k1 > k0, b23 = k3 > k2;
-    const uint64_t m01 = b01 ? k1 : k0, m23 = b23 ? k3 : k2;
-    const int i01 = b01 ? c + 1 : c, i23 = b23 ? c + 3 : c + 2;  // selected with the values: the predicates die here
-    const bool b = m23 > m01;
-    const uint64_t mk = b ? m23 : m01;
-    const int im = b ? i23 : i01;
+    TKNN_MAX2(k0, c, k1, c + 1, m01, i01)
+    TKNN_MAX2(k2, c + 2, k3, c + 3, m23, i23)
+    TKNN_MAX2(m01, i01, m23, i23, m03, i03)
+    uint64_t mk = m03;
+    int im = i03;
+    if (PAD_D == 8) {
+      const uint64_t k4 = p[128], k5 = p[160], k6 = p[192], k7 = p[224];
+      TKNN_MAX2(k4, c + 4, k5, c + 5, m45, i45)
+      TKNN_MAX2(k6, c + 6, k7, c + 7, m67, i67)
+      TKNN_MAX2(m45, i45, m67, i67, m47, i47)
+      TKNN_MAX2(m03, i03, m47, i47, m07, i07)
+      mk = m07;
+      im = i07;
+    }
     if (mk <= key) break;
     A[i * 32] = mk;
     i = im;
   }
   A[i * 32] = key;
 }
+#undef TKNN_MAX2
 
 // ---- bounded ASCENDING list of u64 keys in shared memory (slot s of lane l at L[s * 32 + l]) ----
 // Candidates arrive roughly nearest-first, so a new key usually lands near the tail: the backward
@@ -152,13 +192,17 @@ constexpr int LIST_MAX_K = 24;
 // H = sentinel slot of the lane's region; the heap (large k) uses slots 1..k as its 0-based array
 __device__ __forceinline__ uint64_t kl_worst(const uint64_t* H, int k, bool heap) { return heap ? H[32] : H[k * 32]; }
 
-// PADDED: the heap's slots past its last entry hold 0 (cooperative kernel; see heap_sift_root_padded)
+// PADDED: the padded D-ary heap of the cooperative kernel (pheap_*)
 template <bool PADDED = false>
 __device__ __forceinline__ void kl_insert(uint64_t* H, int& cnt, int k, uint64_t key, bool heap) {
   if (heap) {
-    if (cnt < k) heap_push(H + 32, cnt, key);
-    else if (PADDED) heap_sift_root_padded(H + 32, k, key);
-    else heap_sift_root(H + 32, k, key);
+    if (PADDED) {
+      if (cnt < k) pheap_push(H + 32, cnt, key);
+      else pheap_sift_root(H + 32, k, key);
+    } else {
+      if (cnt < k) heap_push(H + 32, cnt, key);
+      else heap_sift_root(H + 32, k, key);
+    }
   } else {
     list_insert(H, cnt, k, key);
   }
@@ -171,7 +215,8 @@ __device__ __forceinline__ void kl_emit(uint64_t* H, int cnt, int k, bool heap, 
   if (heap) {
     uint64_t* A = H + 32;
     if (PADDED && cnt < k) {  // a short heap (capped final round): slots past it may hold an earlier group's keys
-      A[cnt * 32] = 0; A[(cnt + 1) * 32] = 0; A[(cnt + 2) * 32] = 0;
+      const int last_slot = k - 1 + heap_pads(k);
+      for (int j = cnt; j < cnt + PAD_D - 1 && j <= last_slot; ++j) A[j * 32] = 0;
     }
     for (int i = cnt - 1; i >= 0; --i) {
       const uint64_t top = A[0];
@@ -180,7 +225,7 @@ __device__ __forceinline__ void kl_emit(uint64_t* H, int cnt, int k, bool heap, 
       if (PADDED) {
         const uint64_t last = A[i * 32];
         A[i * 32] = 0;  // the vacated slot joins the zero padding
-        if (i > 0) heap_sift_root_padded(A, i, last);
+        if (i > 0) pheap_sift_root(A, i, last);
       } else if (i > 0) {
         heap_sift_root(A, i, A[i * 32]);
       }
@@ -194,8 +239,8 @@ __device__ __forceinline__ void kl_emit(uint64_t* H, int cnt, int k, bool heap, 
   }
 }
 
-// k-list slots per lane in the cooperative kernel: sentinel + k entries, + 3 zero slots behind a heap
-__host__ __device__ inline int klist_slots(int k) { return k > LIST_MAX_K ? k + 4 : k + 1; }
+// k-list slots per lane in the cooperative kernel: sentinel + k entries, + heap_pads(k) zero slots behind a heap
+__host__ __device__ inline int klist_slots(int k) { return k > LIST_MAX_K ? k + 1 + heap_pads(k) : k + 1; }
 
 __host__ __device__ inline size_t smem_per_warp(int k) {
   return (size_t)klist_slots(k) * 32 * sizeof(uint64_t) + 2 * MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int);
@@ -296,7 +341,7 @@ __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
 
   unsigned long long c_nodes = 0, c_tests = 0, c_ins = 0, c_wnodes = 0, c_wleaves = 0, c_wpts = 0, c_viol = 0;
   if (HEAP && MODE == MODE_KNN) {  // zero padding behind the heap (never written again)
-    H[(k + 1) * 32] = 0; H[(k + 2) * 32] = 0; H[(k + 3) * 32] = 0;
+    for (int j = 0; j < heap_pads(k); ++j) H[(k + 1 + j) * 32] = 0;
   }
 
   for (;;) {
