@@ -42,6 +42,52 @@ def test_kdtree_equals_brute_adversarial(oracle):
             assert (ib == ik).all() and (db == dk).all(), (name, k)
 
 
+def _numpy_d2(x):
+    """The fma-chain d2 of every pair, emulated exactly in float64: differences, products and two-term sums of
+    float32 values are exact in float64, so rounding to float32 after each step reproduces fmaf bit for bit."""
+    xd = x.astype(np.float64)
+    d = (xd[:, None, :] - xd[None, :, :]).astype(np.float32).astype(np.float64)     # dx, dy, dz rounded to fp32
+    acc = (d[..., 0] * d[..., 0]).astype(np.float32).astype(np.float64)              # dx * dx
+    acc = (d[..., 1] * d[..., 1] + acc).astype(np.float32).astype(np.float64)        # fmaf(dy, dy, .)
+    return (d[..., 2] * d[..., 2] + acc).astype(np.float32)                          # fmaf(dz, dz, .)
+
+
+def test_oracle_properties_hypothesis(oracle):
+    """Property test (hypothesis): on small tie-heavy clouds (coordinates on a coarse grid, duplicates, 2-D) the
+    brute-force oracle, the kd-tree oracle and an independent numpy restatement agree bit for bit, rows ascend
+    in (d2, index), and range_count equals the number of pairs within the radius."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(st.integers(8, 120), st.integers(1, 7), st.integers(2, 9), st.booleans(), st.integers(0, 2 ** 31 - 1))
+    def run(n, k, grid, planar, seed):
+        rng = np.random.default_rng(seed)
+        x = (rng.integers(0, grid, (n, 3)) / np.float32(grid - 1)).astype(np.float32)
+        x += (rng.random((n, 3)) < 0.3) * rng.random((n, 3)).astype(np.float32) * np.float32(1e-3)  # a few off-grid points
+        if planar:
+            x[:, 2] = 0
+        x = np.ascontiguousarray(x, np.float32)
+        ib, db = oracle.knn_brute(x, k)
+        ik, dk = oracle.knn_kdtree(x, k)
+        assert (ib == ik).all() and (db == dk).all()
+        # independent restatement: (d2, index) keys, self excluded by index
+        d2 = _numpy_d2(x)
+        keys = (d2.view(np.uint32).astype(np.uint64) << np.uint64(32)) | np.arange(n, dtype=np.uint64)[None, :]
+        keys[np.arange(n), np.arange(n)] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        order = np.argsort(keys, axis=1, kind="stable")[:, :k]
+        assert (ib == order.astype(np.int32)).all()
+        nd2 = np.take_along_axis(d2, order, 1)
+        assert (db == np.sqrt(nd2)).all()                              # sqrtf is correctly rounded on both sides
+        assert (np.diff(nd2, axis=1) >= 0).all()
+        assert (np.diff(ib, axis=1)[np.diff(nd2, axis=1) == 0] > 0).all()   # equal d2 => ascending index
+        r = np.float32(db[:, -1].max())
+        within = d2 <= r * r
+        within[np.arange(n), np.arange(n)] = False
+        assert (oracle.range_count(x, float(r)) == within.sum(1)).all()
+
+    run()
+
+
 def test_lattice_known_answers(oracle):
     """Hand-computable: interior lattice point has 6 neighbours at 1, 12 at sqrt 2, 8 at sqrt 3."""
     m = 7
