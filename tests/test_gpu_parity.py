@@ -524,3 +524,19 @@ def test_round_kernels_agree(oracle, wmax):
             t.set_option("counters", 1)
             t.search(12)
             assert t.stats()["heap_inserts"] >= 12 * x.shape[0]
+
+
+@pytest.mark.parametrize("case", ["uniform", "lidar", "lattice", "dups"])
+def test_committed_golden_vectors(knn, case):
+    """The CUDA path against the committed fixtures (tests/golden/knn_golden.npz, written by the brute-force
+    oracle through tests/golden/make_golden.py): indices bit-exact, distances bit-exact (sqrtf of the same d2)."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "knn_golden.npz"))
+    x, k = np.ascontiguousarray(g[f"{case}_x"], np.float32), int(g[f"{case}_k"])
+    idx, dist = knn.build(x).search(k)
+    assert (idx == g[f"{case}_idx"]).all()
+    assert (dist == g[f"{case}_dist"]).all()
+    # and from a tiny start radius (many rounds), same answer
+    idx2, dist2 = knn.search(k, 1e-4)
+    assert (idx2 == g[f"{case}_idx"]).all() and (dist2 == g[f"{case}_dist"]).all()
