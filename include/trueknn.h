@@ -45,7 +45,7 @@ enum {
   TKNN_EINVAL = 1, /* bad argument (k >= n, dim not 2|3, non-finite coordinate, ...) */
   TKNN_ENOMEM = 2, /* host or device allocation failed */
   TKNN_ECUDA = 3,  /* CUDA runtime error (text in tknn_last_error) */
-  TKNN_ENCCL = 4,  /* reserved for the multi-GPU drivers */
+  TKNN_ENCCL = 4,  /* NCCL error, or libnccl.so.2 could not be loaded (multi-GPU calls only) */
   TKNN_ESTATE = 5  /* call order (search before build, ...) */
 };
 
@@ -193,6 +193,102 @@ TKNN_API int tknn_get_stats(const tknn_ctx* ctx, tknn_stats* out);
 TKNN_API const char* tknn_last_error(const tknn_ctx* ctx);
 TKNN_API int tknn_version(void);
 
+/* ================================ multi-GPU ================================
+ * The reference's multi-GPU model is "replicate every object on every device and split the launch"
+ * (owl/RayGen.cpp:150-200, owl/Context.cpp:75-120), created from a device list (owlContextCreate(ids, n),
+ * owl/include/owl/owl_host.h:360) and unused by its sample (hostCode.cpp:141 passes one device).  Both
+ * variants below live INSIDE the library, over NCCL (NVLink 5 / NVSwitch):
+ *
+ *   TKNN_SHARD_QUERIES    the BVH is replicated on every GPU, GPU g answers the g-th contiguous Morton slice of
+ *                         the queries; no collective on the search path (one all-gather of the points at build).
+ *   TKNN_PARTITION_POINTS every GPU owns one Morton range of the points (clouds that should not be replicated):
+ *                         redistribution by Morton range, local LBVH, local search, boundary-query exchange,
+ *                         remote bounded search, partial top-k merge on (d2, GLOBAL index).
+ *
+ * Two ways in: (a) ONE PROCESS drives all devices — tknn_create_multi (ncclCommInitAll inside) + tknn_multi_build
+ * + tknn_multi_search, host arrays in, host arrays in FILE order out: the drop-in for the sample; (b) ONE RANK
+ * PER PROCESS (torchrun, MPI): every rank creates its own tknn_ctx, rank 0 makes a unique id, everyone calls
+ * tknn_comm_init, then the per-rank calls below; results stay sharded on the ranks.
+ * Collective calls must be made by every rank in the same order.  NCCL failures return TKNN_ENCCL. */
+
+enum { TKNN_SHARD_QUERIES = 1, TKNN_PARTITION_POINTS = 2 };
+
+#define TKNN_UNIQUE_ID_BYTES 128
+
+typedef struct tknn_dist_stats {
+  int32_t n_ranks, rank;
+  uint64_t n_global, n_owned;
+  /* build, ms between CUDA events on this rank's stream (time spent waiting for peers inside a collective included) */
+  float h2d_ms;          /* staging of this rank's slice (0 for device input)                              */
+  float allgather_ms;    /* replicated build: the one all-gather of the points                             */
+  float box_ms;          /* partitioned build: global box (local reduce + all-reduce)                      */
+  float codes_ms;        /* Morton codes on the global grid + cell histogram + its all-reduce              */
+  float splitters_ms;    /* histogram read-back and the host's splitter choice                             */
+  float bucket_ms;       /* destination ranks, one onesweep pass on them, row packing                      */
+  float exchange_ms;     /* all-to-all of (x, y, z, global id) rows                                        */
+  float lbvh_ms;         /* the local (or replicated) LBVH build                                           */
+  float summaries_ms;    /* per-cell boxes + all-gather                                                    */
+  float build_total_ms;
+  /* partitioned search */
+  float local_search_ms, reach_ms, exchange_out_ms, remote_search_ms, exchange_back_ms, merge_ms, finish_ms, d2h_ms;
+  float search_total_ms; /* first launch -> last result written on the device                              */
+  uint64_t boundary_sent, boundary_received;
+  uint64_t bytes_sent_build, bytes_sent_search; /* bytes this rank handed to NCCL (self copies excluded)   */
+} tknn_dist_stats;
+
+/* (b) one rank per process.  tknn_comm_unique_id: rank 0 fills 128 bytes (ncclGetUniqueId) and ships them to the
+ * other ranks by any means; tknn_comm_init: ncclCommInitRank on the context's device. */
+TKNN_API int tknn_comm_unique_id(void* id128_out);
+TKNN_API int tknn_comm_init(tknn_ctx* ctx, int n_ranks, int rank, const void* id128);
+TKNN_API int tknn_get_dist_stats(const tknn_ctx* ctx, tknn_dist_stats* out);
+
+/* TKNN_SHARD_QUERIES build: this rank holds rows [first, first + n_local) of the n_total-point cloud (host or
+ * device); slices must tile the cloud in rank order.  Uploads the slice, assembles the cloud on every GPU with one
+ * ncclAllGather, builds the replicated LBVH.  Search with tknn_search_shard(ctx, k, r, rank, n_ranks, ...). */
+TKNN_API int tknn_build_replicated(tknn_ctx* ctx, const float* xyz_local, uint64_t n_local, uint64_t first,
+                                   uint64_t n_total, int dim, int stride_floats);
+
+/* TKNN_PARTITION_POINTS build: this rank STARTS with rows of global indices [first_index, first_index + n_local)
+ * (host or device) and ENDS owning one Morton range of the global cloud (tknn_partition_owned rows).  Global
+ * indices must stay below 2^31. */
+TKNN_API int tknn_partition_build(tknn_ctx* ctx, const float* xyz_local, uint64_t n_local, uint64_t first_index, int dim,
+                                  int stride_floats);
+TKNN_API uint64_t tknn_partition_owned(const tknn_ctx* ctx);
+
+/* Exact kNN of the owned points against the GLOBAL cloud.  Row r: gid_out[r] = global index of the query,
+ * idx_out[r*k..] = global neighbour indices, dist_out[r*k..] = distances (d2 while TKNN_OPT_SQUARED_DIST is set).
+ * Arrays (host or device) hold `capacity` >= tknn_partition_owned rows; *n_out rows are written. */
+TKNN_API int tknn_partition_search(tknn_ctx* ctx, int k, float start_radius, int32_t* gid_out, int32_t* idx_out,
+                                   float* dist_out, uint64_t capacity, uint64_t* n_out);
+
+/* Proof at sizes no replica fits (2 B points): every rank samples `samples` of its result rows, all ranks brute-force
+ * ALL sampled queries against their OWN points (exact tiled kernel, no BVH), the partial lists are all-gathered and
+ * merged on (d2, global index), and each rank compares its rows bit for bit.  gid/idx/dist: the arrays
+ * tknn_partition_search filled (n_rows rows).  *n_checked / *n_bad: GLOBAL sums (identical on every rank). */
+TKNN_API int tknn_partition_verify(tknn_ctx* ctx, int k, int samples, const int32_t* gid, const int32_t* idx, const float* dist,
+                                   uint64_t n_rows, uint64_t* n_checked, uint64_t* n_bad);
+
+/* (a) one process, all devices.  device_ids: CUDA ordinals (owlContextCreate's device list); distinct devices talk
+ * over NCCL (ncclCommInitAll); a list that NAMES ONE DEVICE SEVERAL TIMES runs that many ranks on it over an
+ * in-process transport (device-to-device copies) — NCCL refuses two ranks on one GPU — which is how the single-GPU
+ * test suite exercises the multi-rank paths.  mode: TKNN_SHARD_QUERIES | TKNN_PARTITION_POINTS. */
+typedef struct tknn_multi tknn_multi;
+TKNN_API int tknn_create_multi(const int* device_ids, int n_devices, int mode, tknn_multi** out);
+TKNN_API int tknn_multi_destroy(tknn_multi* m);
+TKNN_API int tknn_multi_set_option(tknn_multi* m, int key, int64_t value); /* applied to every rank's context */
+/* xyz: n host rows; replaces the same calls as tknn_build on every device */
+TKNN_API int tknn_multi_build(tknn_multi* m, const float* xyz, uint64_t n, int dim, int stride_floats);
+/* idx_out / dist_out: HOST arrays, n*k each, rows in build (file) order — the layout of tknn_search.  Every rank
+ * writes its result rows straight into the owner GPU's slice of the file-order array through peer pointers (P2P
+ * stores over NVLink), then each GPU copies its contiguous slice to the host. */
+TKNN_API int tknn_multi_search(tknn_multi* m, int k, float start_radius, int32_t* idx_out, float* dist_out);
+TKNN_API int tknn_multi_ranks(const tknn_multi* m);
+TKNN_API tknn_ctx* tknn_multi_ctx(tknn_multi* m, int rank); /* per-rank context: stats, options (owned by m) */
+TKNN_API const char* tknn_multi_last_error(const tknn_multi* m);
+/* wall-clock phases of the last tknn_multi_build / tknn_multi_search (ms): [0] build, [1] search (all ranks done),
+ * [2] row exchange to the owners, [3] device->host copies */
+TKNN_API int tknn_multi_get_times(const tknn_multi* m, float* ms4);
+
 /* ---- introspection used by the tests and the bench (not part of the drop-in surface) ---- */
 
 /* Stand-alone onesweep radix sort of (u64 key, u32 value) pairs, stable, in place; device or host
@@ -224,7 +320,9 @@ TKNN_API int tknn_generate_uniform(tknn_ctx* ctx, uint64_t seed, uint64_t first,
 
 /* Point-file ingest and neighbour writer (host only, no CUDA).
  * tknn_read_points: the sample's file grammar (hostCode.cpp:83-124), mmap + parallel parse; names
- * ending in ".f32" are raw little-endian float32 rows of `dim`.  xyz_out: n_cap rows of 3 floats.
+ * ending in ".f32" are raw little-endian float32 rows of `dim`.  xyz_out: n_cap rows of 3 floats; when the rows do
+ * not fit (the grammar consumes the last line whole, so more than n rows can come back) the call returns
+ * TKNN_EINVAL with *n_out = the capacity needed.
  * tknn_write_neighbours: `query,neighbourIndex,distance` lines (the dump commented out at
  * hostCode.cpp:312-319), or raw arrays (path + ".idx.i32" / ".dist.f32") when binary != 0. */
 TKNN_API int tknn_read_points(const char* path, uint64_t n, int dim, float* xyz_out, uint64_t n_cap, uint64_t* n_out);

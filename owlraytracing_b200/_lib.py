@@ -70,6 +70,23 @@ class Stats(C.Structure):
         return d
 
 
+class DistStats(C.Structure):
+    """tknn_dist_stats (include/trueknn.h)."""
+    _fields_ = [("n_ranks", C.c_int32), ("rank", C.c_int32), ("n_global", C.c_uint64), ("n_owned", C.c_uint64)] + [
+        (name, C.c_float) for name in (
+            "h2d_ms", "allgather_ms", "box_ms", "codes_ms", "splitters_ms", "bucket_ms", "exchange_ms", "lbvh_ms",
+            "summaries_ms", "build_total_ms", "local_search_ms", "reach_ms", "exchange_out_ms", "remote_search_ms",
+            "exchange_back_ms", "merge_ms", "finish_ms", "d2h_ms", "search_total_ms")] + [
+        ("boundary_sent", C.c_uint64), ("boundary_received", C.c_uint64), ("bytes_sent_build", C.c_uint64),
+        ("bytes_sent_search", C.c_uint64)]
+
+    def as_dict(self) -> dict:
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+SHARD_QUERIES, PARTITION_POINTS = 1, 2
+UNIQUE_ID_BYTES = 128
+
 # every symbol include/trueknn.h declares (tests check the library exports all of them)
 EXPORTS = [
     "tknn_create", "tknn_destroy", "tknn_set_stream", "tknn_set_option", "tknn_build", "tknn_search",
@@ -77,6 +94,10 @@ EXPORTS = [
     "tknn_brute_force", "tknn_merge_topk", "tknn_get_stats", "tknn_last_error", "tknn_version", "tknn_sort_pairs",
     "tknn_get_bvh", "tknn_generate_uniform", "tknn_measure_bandwidth", "tknn_morton_codes",
     "tknn_read_points", "tknn_write_neighbours", "tknn_reach_mask",
+    "tknn_comm_unique_id", "tknn_comm_init", "tknn_get_dist_stats", "tknn_build_replicated", "tknn_partition_build",
+    "tknn_partition_owned", "tknn_partition_search", "tknn_partition_verify", "tknn_create_multi", "tknn_multi_destroy",
+    "tknn_multi_set_option", "tknn_multi_build", "tknn_multi_search", "tknn_multi_ranks", "tknn_multi_ctx",
+    "tknn_multi_last_error", "tknn_multi_get_times",
 ]
 
 _lib = None
@@ -120,5 +141,25 @@ def load() -> C.CDLL:
     L.tknn_write_neighbours.argtypes = [C.c_char_p, vp, vp, u64, C.c_int, C.c_int]
     L.tknn_measure_bandwidth.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int),
                                          C.POINTER(u64)]
+    L.tknn_comm_unique_id.argtypes = [vp]
+    L.tknn_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.tknn_get_dist_stats.argtypes = [vp, C.POINTER(DistStats)]
+    L.tknn_build_replicated.argtypes = [vp, vp, u64, u64, u64, C.c_int, C.c_int]
+    L.tknn_partition_build.argtypes = [vp, vp, u64, u64, C.c_int, C.c_int]
+    L.tknn_partition_owned.restype = u64
+    L.tknn_partition_owned.argtypes = [vp]
+    L.tknn_partition_search.argtypes = [vp, C.c_int, f32, vp, vp, vp, u64, C.POINTER(u64)]
+    L.tknn_partition_verify.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, u64, C.POINTER(u64), C.POINTER(u64)]
+    L.tknn_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(vp)]
+    L.tknn_multi_destroy.argtypes = [vp]
+    L.tknn_multi_set_option.argtypes = [vp, C.c_int, C.c_int64]
+    L.tknn_multi_build.argtypes = [vp, vp, u64, C.c_int, C.c_int]
+    L.tknn_multi_search.argtypes = [vp, C.c_int, f32, vp, vp]
+    L.tknn_multi_ranks.argtypes = [vp]
+    L.tknn_multi_ctx.restype = vp
+    L.tknn_multi_ctx.argtypes = [vp, C.c_int]
+    L.tknn_multi_last_error.restype = C.c_char_p
+    L.tknn_multi_last_error.argtypes = [vp]
+    L.tknn_multi_get_times.argtypes = [vp, C.POINTER(f32)]
     _lib = L
     return L

@@ -13,7 +13,7 @@ namespace brute {
 
 // Finds the sorted position of each requested original index: ids_sorted ascending, nq entries.
 // qpts[rank] = (x, y, z, original index bits).
-__global__ void __launch_bounds__(256) lookup_queries_kernel(const float4* __restrict__ pts, uint64_t n,
+static __global__ void __launch_bounds__(256) lookup_queries_kernel(const float4* __restrict__ pts, uint64_t n,
                                                              const int32_t* __restrict__ ids_sorted, uint32_t nq,
                                                              float4* __restrict__ qpts) {
   const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) lookup_queries_kernel(const float4* __res
 
 // One warp per (group of 32 queries, split of the point range).  partial[(split * nq + q) * k + i]
 // receives the ascending key list (~0 = empty slot).
-__global__ void __launch_bounds__(32) brute_kernel(const float4* __restrict__ pts, uint64_t n,
+static __global__ void __launch_bounds__(32) brute_kernel(const float4* __restrict__ pts, uint64_t n,
                                                    const float4* __restrict__ qpts, uint32_t nq, int k, int splits,
                                                    uint64_t* __restrict__ partial) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -89,9 +89,9 @@ __global__ void __launch_bounds__(32) brute_kernel(const float4* __restrict__ pt
 
 // Merge `parts` ascending key lists per query into one; writes (idx, sqrt(d2)) rows.
 // row_of[q] (optional) redirects the output row.
-__global__ void __launch_bounds__(32) merge_keys_kernel(const uint64_t* __restrict__ partial, int parts, uint32_t nq, int k,
-                                                        const uint32_t* __restrict__ row_of, int32_t* __restrict__ idx_out,
-                                                        float* __restrict__ dist_out) {
+static __global__ void __launch_bounds__(32) merge_keys_kernel(const uint64_t* __restrict__ partial, int parts, uint32_t nq, int k,
+                                                        const uint32_t* __restrict__ row_of, int squared,
+                                                        int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x;
   uint64_t* H = reinterpret_cast<uint64_t*>(smem) + lane;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(32) merge_keys_kernel(const uint64_t* __restri
   for (int i = cnt - 1; i >= 0; --i) {
     const uint64_t top = H[0];
     io[i] = key_idx(top);
-    dd[i] = __fsqrt_rn(key_d2(top));
+    dd[i] = squared ? key_d2(top) : __fsqrt_rn(key_d2(top));
     if (i > 0) trav::heap_sift_root(H, i, H[i * 32]);
   }
 }
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(32) merge_keys_kernel(const uint64_t* __restri
 // carry SQUARED distances (contexts run with TKNN_OPT_SQUARED_DIST = 1): sqrtf maps two adjacent
 // d2 values to one float about half of the time, so ordering on the reported distance would not
 // be the (d2, index) order.  Duplicates by index are dropped; the output distance is sqrtf(d2).
-__global__ void __launch_bounds__(32) merge_lists_kernel(const int32_t* __restrict__ idx_parts,
+static __global__ void __launch_bounds__(32) merge_lists_kernel(const int32_t* __restrict__ idx_parts,
                                                          const float* __restrict__ dist_parts, int parts, uint32_t nq, int k,
                                                          int squared, int32_t* __restrict__ idx_out,
                                                          float* __restrict__ dist_out) {
@@ -160,12 +160,12 @@ __global__ void __launch_bounds__(32) merge_lists_kernel(const int32_t* __restri
 }
 
 // small gathers used by tknn_query to follow the Morton order of the queries
-__global__ void __launch_bounds__(256) gather_i32_kernel(const int32_t* __restrict__ in, const uint32_t* __restrict__ order,
+static __global__ void __launch_bounds__(256) gather_i32_kernel(const int32_t* __restrict__ in, const uint32_t* __restrict__ order,
                                                          uint64_t n, int32_t* __restrict__ out) {
   const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
   if (i < n) out[i] = in[order[i]];
 }
-__global__ void __launch_bounds__(256) gather_r2_kernel(const float* __restrict__ radius2, const uint32_t* __restrict__ order,
+static __global__ void __launch_bounds__(256) gather_r2_kernel(const float* __restrict__ radius2, const uint32_t* __restrict__ order,
                                                         uint64_t n, float* __restrict__ r2_out) {
   const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
   if (i < n) {
@@ -179,18 +179,11 @@ __global__ void __launch_bounds__(256) gather_r2_kernel(const float* __restrict_
 // global cubic grid, cell id = the top 3*bits bits of the Morton code).  A ball only touches the cells
 // between the cells of its two extreme corners — computed with the builder's own monotone quantiser, so
 // no point of the ball can lie in a cell outside that range — usually 1..8 of them.  mask bit s = rank s.
-__global__ void __launch_bounds__(256) reach_mask_kernel(const float* __restrict__ xyz, uint64_t n, int stride,
-                                                         const float* __restrict__ reach2, const float* __restrict__ box6,
-                                                         const float* __restrict__ summ, int n_ranks, int bits, int self_rank,
-                                                         uint32_t* __restrict__ mask_out) {
-  const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i >= n) return;
+__device__ __forceinline__ uint32_t reach_mask_of(float qx, float qy, float qz, float r2, const float* __restrict__ box6,
+                                                  const float* __restrict__ summ, int n_ranks, int bits, int self_rank) {
   const float lx = box6[0], ly = box6[1], lz = box6[2];
   const float ext = fmaxf(fmaxf(box6[3] - lx, box6[4] - ly), fmaxf(box6[5] - lz, FLT_MIN));
   const float scale = 2097152.0f / ext;  // identical to morton_kernel
-  const float* p = xyz + i * (uint64_t)stride;
-  const float qx = p[0], qy = p[1], qz = p[2];
-  const float r2 = reach2[i];
   const int cells = 1 << bits, shift = 21 - bits;
   int c0[3] = {0, 0, 0}, c1[3] = {cells - 1, cells - 1, cells - 1};
   const float rho = __fmul_rn(__fsqrt_ru(r2), 1.000001f);
@@ -219,11 +212,21 @@ __global__ void __launch_bounds__(256) reach_mask_kernel(const float* __restrict
           if (dx * dx + dy * dy + dz * dz <= lim) mask |= 1u << s;  // an empty (inverted) box gives +inf
         }
       }
-  mask_out[i] = mask;
+  return mask;
+}
+
+static __global__ void __launch_bounds__(256) reach_mask_kernel(const float* __restrict__ xyz, uint64_t n, int stride,
+                                                         const float* __restrict__ reach2, const float* __restrict__ box6,
+                                                         const float* __restrict__ summ, int n_ranks, int bits, int self_rank,
+                                                         uint32_t* __restrict__ mask_out) {
+  const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float* p = xyz + i * (uint64_t)stride;
+  mask_out[i] = reach_mask_of(p[0], p[1], p[2], reach2[i], box6, summ, n_ranks, bits, self_rank);
 }
 
 // u(i, a) = (mix64(seed ^ ((3 i + a) * phi64)) >> 40) * 2^-24  in [0, 1)   
-__global__ void __launch_bounds__(256) generate_uniform_kernel(uint64_t seed, uint64_t first, uint64_t n,
+static __global__ void __launch_bounds__(256) generate_uniform_kernel(uint64_t seed, uint64_t first, uint64_t n,
                                                                float* __restrict__ xyz) {
   const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
   if (t >= 3 * n) return;
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(256) generate_uniform_kernel(uint64_t seed, ui
 }
 
 // read-bandwidth probe: sums `words` uint4 per pass, `passes` passes
-__global__ void __launch_bounds__(256) read_probe_kernel(const uint4* __restrict__ buf, uint64_t words, int passes,
+static __global__ void __launch_bounds__(256) read_probe_kernel(const uint4* __restrict__ buf, uint64_t words, int passes,
                                                          uint32_t* __restrict__ sink) {
   uint32_t acc = 0;
   const uint64_t step = (uint64_t)gridDim.x * 256;

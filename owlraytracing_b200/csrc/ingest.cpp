@@ -59,7 +59,9 @@ void parse_chunk(const char* p, const char* end, Chunk& out) {
 extern "C" {
 
 // Reads up to n points of `dim` (2|3) coordinates from a text file (or raw little-endian float32 rows
-// when the name ends in ".f32") into xyz_out (n_cap rows of 3 floats).  *n_out = points read.
+// when the name ends in ".f32") into xyz_out (n_cap rows of 3 floats).  *n_out = points read.  The last line read
+// is consumed whole (hostCode.cpp:92), so a file with several points per line can yield more than n rows: when they
+// do not fit, the call returns TKNN_EINVAL with *n_out = the rows it needs (0 for every other failure).
 TKNN_API int tknn_read_points(const char* path, uint64_t n, int dim, float* xyz_out, uint64_t n_cap, uint64_t* n_out) {
   if (!path || !xyz_out || !n_out || (dim != 2 && dim != 3)) return TKNN_EINVAL;
   *n_out = 0;
@@ -76,7 +78,7 @@ TKNN_API int tknn_read_points(const char* path, uint64_t n, int dim, float* xyz_
   const size_t plen = strlen(path);
   if (plen > 4 && strcmp(path + plen - 4, ".f32") == 0) {
     const uint64_t rows = std::min<uint64_t>(n, size / (sizeof(float) * (size_t)dim));
-    if (rows > n_cap) rc = TKNN_EINVAL;
+    if (rows > n_cap) { *n_out = rows; rc = TKNN_EINVAL; }
     else {
       const float* f = reinterpret_cast<const float*>(data);
       for (uint64_t i = 0; i < rows; ++i) {
@@ -120,7 +122,7 @@ TKNN_API int tknn_read_points(const char* path, uint64_t n, int dim, float* xyz_
   }
   if (flat.size() % (size_t)dim) return TKNN_EINVAL;  // the reference throws std::out_of_range here
   const uint64_t rows = flat.size() / (size_t)dim;
-  if (rows > n_cap) return TKNN_EINVAL;
+  if (rows > n_cap) { *n_out = rows; return TKNN_EINVAL; }  // *n_out names the capacity a retry needs
   for (uint64_t i = 0; i < rows; ++i) {
     xyz_out[3 * i] = flat[dim * i];
     xyz_out[3 * i + 1] = flat[dim * i + 1];

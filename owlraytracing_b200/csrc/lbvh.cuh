@@ -18,7 +18,7 @@ constexpr int THREADS = 256;
 // Also flags non-finite coordinates (bad != 0 => tknn_build returns TKNN_EINVAL).
 // bounds[0..2] = ordered(min xyz), bounds[3..5] = ordered(max xyz), bounds[6] = bad flag.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) bounds_kernel(const float* __restrict__ xyz, uint64_t n, int dim, int stride,
+static __global__ void __launch_bounds__(THREADS) bounds_kernel(const float* __restrict__ xyz, uint64_t n, int dim, int stride,
                                                          uint32_t* __restrict__ bounds) {
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
   int bad = 0;
@@ -81,7 +81,7 @@ __device__ __forceinline__ uint64_t spread21(uint32_t v) {
   return x;
 }
 
-__global__ void __launch_bounds__(THREADS) morton_kernel(const float* __restrict__ xyz, uint64_t n, int dim, int stride,
+static __global__ void __launch_bounds__(THREADS) morton_kernel(const float* __restrict__ xyz, uint64_t n, int dim, int stride,
                                                          const uint32_t* __restrict__ bounds, int bits,
                                                          uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   const uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
@@ -101,15 +101,20 @@ __global__ void __launch_bounds__(THREADS) morton_kernel(const float* __restrict
   vals[i] = (uint32_t)i;
 }
 
-// sorted float4 points: (x, y, z, original index bits)
-__global__ void __launch_bounds__(THREADS) gather_points_kernel(const float* __restrict__ xyz, int dim, int stride,
+// sorted float4 points: (x, y, z, id bits).  The id is the row number of the point in the caller's array, or —
+// ids_in_w (point-partitioned driver) — the bits of the row's 4th float, so that a rank's BVH carries GLOBAL ids
+// and its (d2, id) tie-breaks are the global ones.  bad_flag (optional): set when a coordinate is not finite.
+static __global__ void __launch_bounds__(THREADS) gather_points_kernel(const float* __restrict__ xyz, int dim, int stride,
                                                                 const uint32_t* __restrict__ order, uint64_t n,
-                                                                float4* __restrict__ pts) {
+                                                                int ids_in_w, float4* __restrict__ pts,
+                                                                uint32_t* __restrict__ bad_flag = nullptr) {
   const uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
   if (i >= n) return;
   const uint32_t src = order[i];
   const float* p = xyz + (uint64_t)src * (uint64_t)stride;
-  pts[i] = make_float4(p[0], p[1], dim > 2 ? p[2] : 0.0f, __uint_as_float(src));
+  const float x = p[0], y = p[1], z = dim > 2 ? p[2] : 0.0f;
+  if (bad_flag && !(isfinite(x) && isfinite(y) && isfinite(z))) *bad_flag = 1u;
+  pts[i] = make_float4(x, y, z, ids_in_w ? p[3] : __uint_as_float(src));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -122,7 +127,7 @@ __global__ void __launch_bounds__(THREADS) gather_points_kernel(const float* __r
 // (Karras 2012); smaller = stronger split; delta[0] = 0.  It is computed from the keys while staging.
 // Output: one ballot word per 32 boundaries.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) leaf_flag_kernel(const uint64_t* __restrict__ keys, uint64_t n, int leaf_max,
+static __global__ void __launch_bounds__(THREADS) leaf_flag_kernel(const uint64_t* __restrict__ keys, uint64_t n, int leaf_max,
                                                             int policy, uint64_t force_split,
                                                             uint32_t* __restrict__ ballots) {
   // The block's boundaries plus a halo of MAX_LEAF on both sides, staged once in shared memory.  Positions
@@ -217,7 +222,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
   return off + inc - v;
 }
 
-__global__ void __launch_bounds__(THREADS) popc_reduce_kernel(const uint32_t* __restrict__ words, uint64_t nw,
+static __global__ void __launch_bounds__(THREADS) popc_reduce_kernel(const uint32_t* __restrict__ words, uint64_t nw,
                                                               uint32_t* __restrict__ block_sums) {
   __shared__ uint32_t s_warp[THREADS / 32];
   const uint64_t base = (uint64_t)blockIdx.x * SCAN_CHUNK + (uint64_t)threadIdx.x * SCAN_ITEMS;
@@ -231,7 +236,7 @@ __global__ void __launch_bounds__(THREADS) popc_reduce_kernel(const uint32_t* __
 }
 
 // single block: exclusive scan of block_sums in place, grand total -> *total_out
-__global__ void __launch_bounds__(THREADS) scan_sums_kernel(uint32_t* __restrict__ block_sums, uint32_t nb,
+static __global__ void __launch_bounds__(THREADS) scan_sums_kernel(uint32_t* __restrict__ block_sums, uint32_t nb,
                                                             uint32_t* __restrict__ total_out) {
   __shared__ uint32_t s_warp[THREADS / 32];
   uint32_t carry = 0;
@@ -246,7 +251,7 @@ __global__ void __launch_bounds__(THREADS) scan_sums_kernel(uint32_t* __restrict
   if (threadIdx.x == 0) *total_out = carry;
 }
 
-__global__ void __launch_bounds__(THREADS) popc_apply_kernel(const uint32_t* __restrict__ words, uint64_t nw,
+static __global__ void __launch_bounds__(THREADS) popc_apply_kernel(const uint32_t* __restrict__ words, uint64_t nw,
                                                              const uint32_t* __restrict__ block_sums,
                                                              uint32_t* __restrict__ offsets) {
   __shared__ uint32_t s_warp[THREADS / 32];
@@ -267,7 +272,7 @@ __global__ void __launch_bounds__(THREADS) popc_apply_kernel(const uint32_t* __r
 }
 
 // leaf_start[offsets[w] + rank-in-word] = b for every flagged boundary; leaf_key = its Morton code
-__global__ void __launch_bounds__(THREADS) leaf_emit_kernel(const uint32_t* __restrict__ ballots,
+static __global__ void __launch_bounds__(THREADS) leaf_emit_kernel(const uint32_t* __restrict__ ballots,
                                                             const uint32_t* __restrict__ offsets,
                                                             const uint64_t* __restrict__ keys, uint64_t n,
                                                             uint32_t n_leaves, uint32_t* __restrict__ leaf_start,
@@ -296,7 +301,7 @@ __device__ __forceinline__ int karras_delta(const uint64_t* __restrict__ key, in
   return x ? __clzll((long long)x) : 64 + __clz((uint32_t)i ^ (uint32_t)j);
 }
 
-__global__ void __launch_bounds__(THREADS) karras_kernel(const uint64_t* __restrict__ leaf_key,
+static __global__ void __launch_bounds__(THREADS) karras_kernel(const uint64_t* __restrict__ leaf_key,
                                                          const uint32_t* __restrict__ leaf_start, uint32_t n_leaves,
                                                          int4* __restrict__ child_info, int32_t* __restrict__ parent_leaf,
                                                          int32_t* __restrict__ parent_node) {
@@ -348,7 +353,7 @@ __global__ void __launch_bounds__(THREADS) karras_kernel(const uint64_t* __restr
 // and stops; the second one reads it back, writes the whole node in its final interleaved layout
 // (common.cuh: Node) with four 16-byte stores, merges and continues.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) refit_kernel(const float4* __restrict__ pts,
+static __global__ void __launch_bounds__(THREADS) refit_kernel(const float4* __restrict__ pts,
                                                         const uint32_t* __restrict__ leaf_start, uint32_t n_leaves,
                                                         const int4* __restrict__ child_info,
                                                         const int32_t* __restrict__ parent_leaf,
@@ -380,6 +385,7 @@ __global__ void __launch_bounds__(THREADS) refit_kernel(const float4* __restrict
     __stcg(&node_min_idx[2 * node + slot], mn);
     __threadfence();
     if (atomicAdd(&arrive[node], 1u) == 0u) return;
+    __threadfence();  // acquire side: the sibling's record was written before its arrival
     const float4* sib = reinterpret_cast<const float4*>(nodes + node) + 2 * (1 - slot);
     const float4 slo = __ldcg(sib), shi = __ldcg(sib + 1);
     mn = min(mn, __ldcg(&node_min_idx[2 * node + (1 - slot)]));

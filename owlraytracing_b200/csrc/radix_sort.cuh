@@ -21,6 +21,7 @@ constexpr int PASSES = 64 / RADIX_BITS;
 #define TKNN_SORT_ITEMS 16
 #endif
 constexpr int THREADS = TKNN_SORT_THREADS;
+static_assert(THREADS == RADIX, "onesweep_kernel: thread d owns digit d (status, histogram and scatter rows)");
 constexpr int WARPS = THREADS / 32;
 constexpr int ITEMS = TKNN_SORT_ITEMS;      // pairs per thread
 constexpr int TILE = THREADS * ITEMS;       // 4096 pairs per tile
@@ -36,7 +37,7 @@ constexpr size_t DYN_SMEM = (size_t)TILE * (sizeof(uint64_t) + sizeof(uint32_t))
 __host__ __device__ inline uint32_t num_tiles(uint64_t n) { return (uint32_t)((n + TILE - 1) / TILE); }
 
 // hist[pass][digit] += count, all passes in one read of the keys.
-__global__ void __launch_bounds__(THREADS) histogram_kernel(const uint64_t* __restrict__ keys, uint64_t n,
+static __global__ void __launch_bounds__(THREADS) histogram_kernel(const uint64_t* __restrict__ keys, uint64_t n,
                                                             uint32_t* __restrict__ hist) {
   __shared__ uint32_t s_hist[PASSES * RADIX];
   for (int i = threadIdx.x; i < PASSES * RADIX; i += THREADS) s_hist[i] = 0;
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(THREADS) histogram_kernel(const uint64_t* __re
 
 // in-place exclusive scan of each pass's 256 bins: one block per pass.
 // Block 0 also writes the LOOKBACK "prefix 0" rows that sit in front of the tile status array.
-__global__ void __launch_bounds__(RADIX) scan_histogram_kernel(uint32_t* __restrict__ hist, uint32_t* __restrict__ status_pad) {
+static __global__ void __launch_bounds__(RADIX) scan_histogram_kernel(uint32_t* __restrict__ hist, uint32_t* __restrict__ status_pad) {
   __shared__ uint32_t s_warp[RADIX / 32];
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < LOOKBACK * RADIX; i += RADIX) status_pad[i] = FLAG_PREFIX;
@@ -91,7 +92,7 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d) {
 }
 
 // One onesweep pass over digit `shift / 8`.
-__global__ void __launch_bounds__(THREADS, 3)
+static __global__ void __launch_bounds__(THREADS, 3)
     onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                     uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint64_t n, int shift,
                     const uint32_t* __restrict__ bin_offset, uint32_t* status, uint32_t* tile_counter) {

@@ -323,7 +323,7 @@ __device__ __forceinline__ uint32_t filter4(const float* sx, int j0, float2 qx, 
 // tie pruning (chosen by the host when the build found leaves of coincident points).
 // HEAP: k > LIST_MAX_K (compile-time, so the small-k kernel does not carry the heap code).
 template <int MODE, bool COUNT, int VARIANT, bool HEAP>
-__global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
+static __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
   constexpr bool APPROX = VARIANT == 1;
   constexpr bool TIES = VARIANT == 2 && MODE == MODE_KNN;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -562,7 +562,7 @@ constexpr int SPARSE_THREADS = 128;
 __host__ __device__ inline size_t sparse_smem(int k) { return ((size_t)(k + 1) * SPARSE_THREADS + 3 * 32) * sizeof(uint64_t); }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(SPARSE_THREADS) traverse_sparse_kernel(const Params P) {
+static __global__ void __launch_bounds__(SPARSE_THREADS) traverse_sparse_kernel(const Params P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = P.k;
@@ -715,7 +715,7 @@ __device__ __forceinline__ void warp_list_insert(uint64_t* L, int& cnt, int k, u
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(WQ_WARPS * 32) traverse_warp_kernel(const Params P) {
+static __global__ void __launch_bounds__(WQ_WARPS * 32) traverse_warp_kernel(const Params P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = P.k;
@@ -837,7 +837,7 @@ __global__ void __launch_bounds__(WQ_WARPS * 32) traverse_warp_kernel(const Para
 
 // Ballot words of "the point at sorted position p has an original index in [lo, hi)": the first step of
 // cutting the query list into FILE-order slices whose output rows are contiguous (pipelined host output).
-__global__ void __launch_bounds__(256) index_range_flag_kernel(const float4* __restrict__ pts, uint64_t n, uint32_t lo,
+static __global__ void __launch_bounds__(256) index_range_flag_kernel(const float4* __restrict__ pts, uint64_t n, uint32_t lo,
                                                                uint32_t hi, uint32_t* __restrict__ words) {
   const uint64_t p = (uint64_t)blockIdx.x * 256 + threadIdx.x;
   bool in = false;
@@ -853,7 +853,7 @@ __global__ void __launch_bounds__(256) index_range_flag_kernel(const float4* __r
 // Round compaction: unresolved ballot words -> the next round's queue, order preserved (so the
 // next round's groups are still Morton-coherent).  offsets[] = exclusive scan of popc(words).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) compact_queue_kernel(const uint32_t* __restrict__ words,
+static __global__ void __launch_bounds__(256) compact_queue_kernel(const uint32_t* __restrict__ words,
                                                             const uint32_t* __restrict__ offsets, uint32_t n_groups,
                                                             const uint32_t* __restrict__ queue_in, uint64_t q_begin,
                                                             uint32_t* __restrict__ queue_out) {

@@ -17,6 +17,7 @@
 
 #include "brute.cuh"
 #include "common.cuh"
+#include "ctx.cuh"
 #include "lbvh.cuh"
 #include "radix_sort.cuh"
 #include "traverse.cuh"
@@ -24,52 +25,10 @@
 using namespace tknn;
 
 // ---------------------------------------------------------------------------------------------
-// context
+// context helpers (declared in ctx.cuh)
 // ---------------------------------------------------------------------------------------------
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-struct tknn_ctx {
-  int device = 0;
-  int sm_count = 148;
-  size_t l2_bytes = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
-  std::string err;
-  // options
-  int leaf_size = 32, counters = 0, leaf_policy = 0, sample_groups = 128, blocks_per_sm = 0, squared = 0,
-      radius_quantile = 990;
-  // BVH
-  uint64_t n = 0;
-  uint32_t n_leaves = 0;
-  DevBuf pts, nodes, leaf_start, node_min_idx;
-  float scene_box[6] = {0, 0, 0, 0, 0, 0};
-  // search scratch (grown on demand, kept across searches)
-  DevBuf queue_a, queue_b, unresolved, offsets, block_sums, scalars, stage_idx, stage_dist, sample;
-  // build scratch, kept across builds (grow-only) unless keep_scratch == 0
-  DevBuf b_in, b_keys_a, b_keys_b, b_vals_a, b_vals_b, b_sort_tmp, b_delta, b_ballots, b_leaf_key, b_child_info,
-      b_parent_leaf, b_parent_node, b_arrive;
-  int keep_scratch = 1;
-  int sparse_divisor = 8;
-  int warp_round_max = 49152;  // rounds with at most this many active queries run one warp per query (0 = never)
-  int approx_filter = 0;
-  int tie_pruning = 0;        // 0 = auto (on when the build saw leaves of coincident points), 1 = on, 2 = off
-  int morton_bits = 0;        // 0 = auto (ceil(log2 n / 3) + 8, clamped to [10, 21])
-  bool has_dup_leaves = false; // the build found a leaf of coincident points => tie-pruning kernel variant
-  int built_morton_bits = 21; // what the current BVH was built with (queries are coded the same way)
-  int output_chunks = 4;  // host-output pipelining: slices whose D2H overlaps the next slice's search (1 = off)
-  int file_order_chunks = 4;  // same for tknn_search (file-order rows): slices by original index (1 = off)
-  DevBuf chunk_queue;
-  std::vector<cudaEvent_t> chunk_ev;
-  cudaEvent_t ev[8] = {};
-  std::vector<cudaEvent_t> round_ev;
-  tknn_stats stats;
-  tknn_ctx() { std::memset(&stats, 0, sizeof(stats)); }
-};
-
-namespace {
+namespace tknn {
+namespace host {
 
 int fail(tknn_ctx* c, int code, const char* fmt, ...) {
   if (c) {
@@ -82,22 +41,6 @@ int fail(tknn_ctx* c, int code, const char* fmt, ...) {
   }
   return code;
 }
-
-#define TK_CUDA(c, expr)                                                                            \
-  do {                                                                                              \
-    cudaError_t e__ = (expr);                                                                       \
-    if (e__ != cudaSuccess) {                                                                       \
-      cudaGetLastError();                                                                           \
-      return fail((c), e__ == cudaErrorMemoryAllocation ? TKNN_ENOMEM : TKNN_ECUDA, "%s: %s (%s:%d)", #expr, \
-                  cudaGetErrorString(e__), __FILE__, __LINE__);                                     \
-    }                                                                                               \
-  } while (0)
-
-#define TK_TRY(expr)                 \
-  do {                               \
-    int rc__ = (expr);               \
-    if (rc__ != TKNN_OK) return rc__; \
-  } while (0)
 
 int ensure(tknn_ctx* c, DevBuf& b, size_t bytes) {
   if (b.bytes >= bytes && b.p) return TKNN_OK;
@@ -121,17 +64,12 @@ bool is_device_ptr(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-struct ScopedDevice {
-  int prev = -1;
-  explicit ScopedDevice(int d) { cudaGetDevice(&prev); if (prev != d) cudaSetDevice(d); else prev = -1; }
-  ~ScopedDevice() { if (prev >= 0) cudaSetDevice(prev); }
-};
+}  // namespace host
+}  // namespace tknn
 
-inline unsigned blocks_for(uint64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+using namespace tknn::host;
 
-// scalars layout (uint32 words unless noted)
-enum { SC_GROUP_COUNTER = 0, SC_TOTAL = 1, SC_ERROR = 2, SC_BOUNDS = 4 /* 7 words */, SC_SCENE = 12 /* 6 floats */,
-       SC_COUNTERS = 20 /* 8 x u64, 8-byte aligned */, SC_DUPLEAF = 40, SC_WORDS = 44 };
+namespace {
 
 // exclusive scan of popc(words[0..nw)) into offsets, total into scalars[SC_TOTAL]
 int popc_scan(tknn_ctx* c, const uint32_t* words, uint64_t nw, uint32_t* offsets, int* launches) {
@@ -422,10 +360,11 @@ int auto_morton_bits(uint64_t n) {
 int check_ctx(tknn_ctx* c) { return c ? TKNN_OK : TKNN_EINVAL; }
 
 int read_error_flag(tknn_ctx* c) {
-  uint32_t e = 0;
-  TK_CUDA(c, cudaMemcpyAsync(&e, c->scalars.as<uint32_t>() + SC_ERROR, sizeof(e), cudaMemcpyDeviceToHost, c->stream));
+  uint32_t e[2] = {0, 0};  // SC_ERROR, SC_QBAD
+  TK_CUDA(c, cudaMemcpyAsync(e, c->scalars.as<uint32_t>() + SC_ERROR, sizeof(e), cudaMemcpyDeviceToHost, c->stream));
   TK_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (e) return fail(c, TKNN_ECUDA, "traversal stack overflow (BVH deeper than %d)", STACK_DEPTH);
+  if (e[0]) return fail(c, TKNN_ECUDA, "traversal stack overflow (BVH deeper than %d)", STACK_DEPTH);
+  if (e[1]) return fail(c, TKNN_EINVAL, "non-finite coordinate in the query points");
   return TKNN_OK;
 }
 
@@ -468,8 +407,10 @@ void reset_search_stats(tknn_ctx* c) {
   s.d2h_bytes = 0;
 }
 
+}  // namespace
+
 // all-points search over query positions [q_begin, q_begin + nq) of the sorted order
-int search_range(tknn_ctx* c, int k, float start_radius, uint64_t q_begin, uint64_t nq, int row_mode, int32_t* qid_out,
+int tknn::host::search_range(tknn_ctx* c, int k, float start_radius, uint64_t q_begin, uint64_t nq, int row_mode, int32_t* qid_out,
                  int32_t* idx_out, float* dist_out, uint64_t rows) {
   if (c->n == 0) return fail(c, TKNN_ESTATE, "tknn_search before tknn_build");
   if (k < 1 || k > TKNN_MAX_K) return fail(c, TKNN_EINVAL, "k = %d outside [1, %d]", k, TKNN_MAX_K);
@@ -477,6 +418,8 @@ int search_range(tknn_ctx* c, int k, float start_radius, uint64_t q_begin, uint6
                                           (unsigned long long)(c->n - 1));
   if (std::isnan(start_radius)) return fail(c, TKNN_EINVAL, "start_radius is NaN");
   if (!idx_out || !dist_out) return fail(c, TKNN_EINVAL, "null output array");
+  if (c->ids_in_w && row_mode == 0)
+    return fail(c, TKNN_ESTATE, "this BVH carries caller-chosen point ids (point-partitioned build): rows in build order do not exist");
   reset_search_stats(c);
   c->stats.n_queries = nq;
   c->stats.k = k;
@@ -498,7 +441,7 @@ int search_range(tknn_ctx* c, int k, float start_radius, uint64_t q_begin, uint6
     d_dist = c->stage_dist.as<float>();
   }
 
-  TK_CUDA(c, cudaMemsetAsync(sc + SC_ERROR, 0, sizeof(uint32_t), c->stream));
+  TK_CUDA(c, cudaMemsetAsync(sc + SC_ERROR, 0, 2 * sizeof(uint32_t), c->stream));
   TK_CUDA(c, cudaMemsetAsync(sc + SC_COUNTERS, 0, 8 * sizeof(unsigned long long), c->stream));
   TK_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
   int launches = 0;
@@ -640,8 +583,6 @@ int search_range(tknn_ctx* c, int k, float start_radius, uint64_t q_begin, uint6
   return TKNN_OK;
 }
 
-}  // namespace
-
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
@@ -682,10 +623,13 @@ int tknn_destroy(tknn_ctx* c) {
   if (!c) return TKNN_EINVAL;
   ScopedDevice sd(c->device);
   cudaStreamSynchronize(c->stream);
+  tknn_internal_free_dist(c);
   for (DevBuf* b : {&c->pts, &c->nodes, &c->leaf_start, &c->node_min_idx, &c->queue_a, &c->queue_b, &c->unresolved, &c->offsets,
                     &c->block_sums, &c->scalars, &c->stage_idx, &c->stage_dist, &c->sample, &c->chunk_queue, &c->b_in, &c->b_keys_a,
                     &c->b_keys_b, &c->b_vals_a, &c->b_vals_b, &c->b_sort_tmp, &c->b_delta, &c->b_ballots, &c->b_leaf_key,
-                    &c->b_child_info, &c->b_parent_leaf, &c->b_parent_node, &c->b_arrive})
+                    &c->b_child_info, &c->b_parent_leaf, &c->b_parent_node, &c->b_arrive, &c->q_stage, &c->q_keys_a, &c->q_keys_b,
+                    &c->q_vals_a, &c->q_vals_b, &c->q_sort_tmp, &c->q_pts, &c->q_sid_stage, &c->q_sid_sorted, &c->q_rad_stage,
+                    &c->q_r2_sorted})
     release(*b);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->round_ev) cudaEventDestroy(ev);
@@ -758,8 +702,15 @@ int tknn_set_option(tknn_ctx* c, int key, int64_t value) {
 }
 
 int tknn_build(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int stride_floats) {
+  return build_core(c, xyz, n, dim, stride_floats, false);
+}
+
+}  // extern "C"
+
+int tknn::host::build_core(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int stride_floats, bool ids_in_w) {
   TK_TRY(check_ctx(c));
   if (!xyz) return fail(c, TKNN_EINVAL, "null point array");
+  if (ids_in_w && (dim != 3 || stride_floats < 4)) return fail(c, TKNN_EINVAL, "ids in w need dim 3 and stride >= 4");
   if (dim != 2 && dim != 3) return fail(c, TKNN_EINVAL, "dim = %d (must be 2 or 3, hostCode.cpp:114-124)", dim);
   if (stride_floats < dim) return fail(c, TKNN_EINVAL, "stride %d < dim %d", stride_floats, dim);
   if (n < 2) return fail(c, TKNN_EINVAL, "need at least 2 points (got %llu)", (unsigned long long)n);
@@ -869,7 +820,7 @@ int tknn_build(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int stride_fl
       ballots.as<uint32_t>(), c->offsets.as<uint32_t>(), skeys, n, m, c->leaf_start.as<uint32_t>(),
       leaf_key.as<uint64_t>());
   lbvh::gather_points_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, dim, stride_floats,
-                                                                                   svals, n, c->pts.as<float4>());
+                                                                                   svals, n, ids_in_w ? 1 : 0, c->pts.as<float4>());
   launches += 2;
   TK_BC(cudaEventRecord(c->ev[5], st));
 
@@ -920,8 +871,11 @@ int tknn_build(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int stride_fl
   S.build_launches = (uint32_t)launches;
   c->n = n;
   c->n_leaves = m;
+  c->ids_in_w = ids_in_w;
   return TKNN_OK;
 }
+
+extern "C" {
 
 int tknn_search(tknn_ctx* c, int k, float start_radius, int32_t* idx_out, float* dist_out) {
   TK_TRY(check_ctx(c));
@@ -985,8 +939,12 @@ int tknn_query(tknn_ctx* c, const float* queries, uint64_t nq, int dim, int stri
   cudaStream_t st = c->stream;
   uint32_t* sc = c->scalars.as<uint32_t>();
 
-  DevBuf q_stage, keys_a, keys_b, vals_a, vals_b, sort_tmp, qpts, sid_stage, sid_sorted, rad_stage, r2_sorted;
+  // scratch lives in the context (grow-only): a call allocates nothing once the buffers have reached their size
+  DevBuf &q_stage = c->q_stage, &keys_a = c->q_keys_a, &keys_b = c->q_keys_b, &vals_a = c->q_vals_a, &vals_b = c->q_vals_b,
+         &sort_tmp = c->q_sort_tmp, &qpts = c->q_pts, &sid_stage = c->q_sid_stage, &sid_sorted = c->q_sid_sorted,
+         &rad_stage = c->q_rad_stage, &r2_sorted = c->q_r2_sorted;
   auto cleanup = [&]() {
+    if (c->keep_scratch) return;
     for (DevBuf* b : {&q_stage, &keys_a, &keys_b, &vals_a, &vals_b, &sort_tmp, &qpts, &sid_stage, &sid_sorted, &rad_stage,
                       &r2_sorted})
       release(*b);
@@ -1023,6 +981,7 @@ int tknn_query(tknn_ctx* c, const float* queries, uint64_t nq, int dim, int stri
   TK_B(ensure(c, sort_tmp, rsort::temp_words(nq) * sizeof(uint32_t)));
   TK_B(ensure(c, qpts, nq * sizeof(float4)));
   int launches = 0;
+  TK_BC(cudaMemsetAsync(sc + SC_ERROR, 0, 2 * sizeof(uint32_t), st));
   const int qbits = c->built_morton_bits;
   lbvh::morton_kernel<<<blocks_for(nq, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_q, nq, dim, stride_floats, sc + SC_BOUNDS, qbits,
                                                                               keys_a.as<uint64_t>(), vals_a.as<uint32_t>());
@@ -1032,7 +991,8 @@ int tknn_query(tknn_ctx* c, const float* queries, uint64_t nq, int dim, int stri
                                 sort_tmp.as<uint32_t>(), c->sm_count, st, (3 * qbits + 7) / 8, &q_in_b);
   const uint32_t* qorder = q_in_b ? vals_b.as<uint32_t>() : vals_a.as<uint32_t>();
   lbvh::gather_points_kernel<<<blocks_for(nq, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_q, dim, stride_floats,
-                                                                                    qorder, nq, qpts.as<float4>());
+                                                                                    qorder, nq, 0, qpts.as<float4>(), sc + SC_QBAD);
+  TK_BC(cudaGetLastError());
   ++launches;
   const int32_t* d_sid_sorted = nullptr;
   const float* d_r2_sorted = nullptr;
@@ -1056,7 +1016,6 @@ int tknn_query(tknn_ctx* c, const float* queries, uint64_t nq, int dim, int stri
   if (!idx_dev) { TK_B(ensure(c, c->stage_idx, out_elems * sizeof(int32_t))); d_idx = c->stage_idx.as<int32_t>(); }
   if (!dist_dev) { TK_B(ensure(c, c->stage_dist, out_elems * sizeof(float))); d_dist = c->stage_dist.as<float>(); }
 
-  TK_BC(cudaMemsetAsync(sc + SC_ERROR, 0, sizeof(uint32_t), st));
   TK_BC(cudaMemsetAsync(sc + SC_COUNTERS, 0, 8 * sizeof(unsigned long long), st));
   float r0 = start_radius;
   // a query set can hold fewer than k reachable neighbours only through self exclusion / radius caps
@@ -1126,7 +1085,7 @@ int tknn_range_count(tknn_ctx* c, float radius, uint32_t* count_out) {
   P.count_out = d_out;
   P.group_counter = sc + SC_GROUP_COUNTER;
   P.counters = c->counters ? reinterpret_cast<unsigned long long*>(sc + SC_COUNTERS) : nullptr;
-  TK_CUDA(c, cudaMemsetAsync(sc + SC_ERROR, 0, sizeof(uint32_t), c->stream));
+  TK_CUDA(c, cudaMemsetAsync(sc + SC_ERROR, 0, 2 * sizeof(uint32_t), c->stream));
   TK_CUDA(c, cudaMemsetAsync(sc + SC_COUNTERS, 0, 8 * sizeof(unsigned long long), c->stream));
   TK_CUDA(c, cudaMemsetAsync(sc + SC_GROUP_COUNTER, 0, sizeof(uint32_t), c->stream));
   TK_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
@@ -1154,6 +1113,7 @@ int tknn_brute_force(tknn_ctx* c, const int32_t* query_ids, uint64_t nq, int k, 
   if (nq == 0) return TKNN_OK;
   if (!query_ids || !idx_out || !dist_out) return fail(c, TKNN_EINVAL, "null array");
   if (nq > (1u << 20)) return fail(c, TKNN_EINVAL, "at most 2^20 brute-force queries per call");
+  if (c->ids_in_w) return fail(c, TKNN_ESTATE, "this BVH carries caller-chosen point ids: use tknn_partition_verify");
   ScopedDevice sd(c->device);
   cudaStream_t st = c->stream;
   std::vector<int32_t> ids(nq);
@@ -1172,17 +1132,14 @@ int tknn_brute_force(tknn_ctx* c, const int32_t* query_ids, uint64_t nq, int k, 
     if (sorted[i] < 0 || (uint64_t)sorted[i] >= c->n) return fail(c, TKNN_EINVAL, "query id %d out of range", sorted[i]);
     if (i && sorted[i] == sorted[i - 1]) return fail(c, TKNN_EINVAL, "duplicate query id %d", sorted[i]);
   }
-  int splits = (int)std::max<uint64_t>(1, std::min<uint64_t>(256, ((uint64_t)c->sm_count * 16) / ((nq + 31) / 32)));
-  splits = (int)std::min<uint64_t>((uint64_t)splits, (c->n + 1023) / 1024);
-  DevBuf d_ids, d_perm, qpts, partial, o_idx, o_dist;
-  auto cleanup = [&]() { for (DevBuf* b : {&d_ids, &d_perm, &qpts, &partial, &o_idx, &o_dist}) release(*b); };
+  DevBuf d_ids, d_perm, qpts, o_idx, o_dist;
+  auto cleanup = [&]() { for (DevBuf* b : {&d_ids, &d_perm, &qpts, &o_idx, &o_dist}) release(*b); };
 #define TK_B(expr) do { int rc_ = (expr); if (rc_ != TKNN_OK) { cleanup(); return rc_; } } while (0)
 #define TK_BC(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cudaGetLastError(); cleanup(); \
     return fail(c, e_ == cudaErrorMemoryAllocation ? TKNN_ENOMEM : TKNN_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); } } while (0)
   TK_B(ensure(c, d_ids, nq * sizeof(int32_t)));
   TK_B(ensure(c, d_perm, nq * sizeof(uint32_t)));
   TK_B(ensure(c, qpts, nq * sizeof(float4)));
-  TK_B(ensure(c, partial, (size_t)splits * nq * k * sizeof(uint64_t)));
   TK_BC(cudaMemcpyAsync(d_ids.p, sorted.data(), nq * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   TK_BC(cudaMemcpyAsync(d_perm.p, perm.data(), nq * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   const bool idx_dev = is_device_ptr(idx_out), dist_dev = is_device_ptr(dist_out);
@@ -1192,15 +1149,7 @@ int tknn_brute_force(tknn_ctx* c, const int32_t* query_ids, uint64_t nq, int k, 
   if (!dist_dev) { TK_B(ensure(c, o_dist, nq * k * sizeof(float))); d_dist = o_dist.as<float>(); }
   brute::lookup_queries_kernel<<<blocks_for(c->n, 256), 256, 0, st>>>(c->pts.as<float4>(), c->n, d_ids.as<int32_t>(),
                                                                        (uint32_t)nq, qpts.as<float4>());
-  const size_t smem = 32 * sizeof(float4) + (size_t)k * 32 * sizeof(uint64_t);
-  TK_BC(cudaFuncSetAttribute(brute::brute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  TK_BC(cudaFuncSetAttribute(brute::merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)((nq + 31) / 32), (unsigned)splits);
-  brute::brute_kernel<<<grid, 32, smem, st>>>(c->pts.as<float4>(), c->n, qpts.as<float4>(), (uint32_t)nq, k, splits,
-                                              partial.as<uint64_t>());
-  brute::merge_keys_kernel<<<(unsigned)((nq + 31) / 32), 32, smem, st>>>(partial.as<uint64_t>(), splits, (uint32_t)nq, k,
-                                                                        d_perm.as<uint32_t>(), d_idx, d_dist);
-  TK_BC(cudaGetLastError());
+  TK_B(brute_core(c, qpts.as<float4>(), nq, k, d_perm.as<uint32_t>(), d_idx, d_dist, 0));
   if (!idx_dev) TK_BC(cudaMemcpyAsync(idx_out, d_idx, nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (!dist_dev) TK_BC(cudaMemcpyAsync(dist_out, d_dist, nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
   TK_BC(cudaStreamSynchronize(st));
@@ -1209,6 +1158,38 @@ int tknn_brute_force(tknn_ctx* c, const int32_t* query_ids, uint64_t nq, int k, 
 #undef TK_BC
   return TKNN_OK;
 }
+
+}  // extern "C"
+
+// Exact tiled brute force of external queries (x, y, z, id to exclude) against the sorted points: one warp per
+// (32 queries, split of the point range), then a per-query merge of the splits.  Fills the grid twice over.
+int tknn::host::brute_core(tknn_ctx* c, const float4* d_qpts, uint64_t nq, int k, const uint32_t* d_row_of, int32_t* d_idx,
+                           float* d_dist, int squared) {
+  if (nq == 0) return TKNN_OK;
+  cudaStream_t st = c->stream;
+  const uint64_t groups = (nq + 31) / 32;
+  int splits = (int)std::max<uint64_t>(1, std::min<uint64_t>(256, ((uint64_t)c->sm_count * 64 + groups - 1) / groups));
+  splits = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)splits, (c->n + 1023) / 1024));
+  DevBuf partial;
+  int rc = ensure(c, partial, (size_t)splits * nq * k * sizeof(uint64_t));
+  if (rc != TKNN_OK) return rc;
+  const size_t smem = 32 * sizeof(float4) + (size_t)k * 32 * sizeof(uint64_t);
+  cudaError_t e = cudaFuncSetAttribute(brute::brute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(brute::merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) {
+    dim3 grid((unsigned)groups, (unsigned)splits);
+    brute::brute_kernel<<<grid, 32, smem, st>>>(c->pts.as<float4>(), c->n, d_qpts, (uint32_t)nq, k, splits, partial.as<uint64_t>());
+    brute::merge_keys_kernel<<<(unsigned)groups, 32, smem, st>>>(partial.as<uint64_t>(), splits, (uint32_t)nq, k, d_row_of, squared,
+                                                                 d_idx, d_dist);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `partial` is released below
+  release(partial);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(c, TKNN_ECUDA, "brute force: %s", cudaGetErrorString(e)); }
+  return TKNN_OK;
+}
+
+extern "C" {
 
 int tknn_merge_topk(tknn_ctx* c, const int32_t* idx_parts, const float* d2_parts, int parts, uint64_t nq, int k,
                     int32_t* idx_out, float* dist_out) {

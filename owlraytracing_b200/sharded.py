@@ -16,9 +16,10 @@ import torch.distributed as dist
 class ShardedTrueKNN:
     """`engine` is a built-or-buildable TrueKNN context (owlraytracing_b200.TrueKNN on this rank's GPU).
 
-    The engine needs: build(points), search_shard(k, shard, n_shards, start_radius) -> (qid, idx, dist),
-    shard_capacity(n_shards).  Tests inject a CPU stand-in to exercise the collective plumbing;
-    the product path always uses the CUDA engine (there is no fallback)."""
+    The engine needs: build(points), build_replicated(slice, first, n_total), search_shard(k, shard, n_shards,
+    start_radius) -> (qid, idx, dist), shard_capacity(n_shards).  Tests inject a CPU stand-in to exercise the
+    bookkeeping; the product path always uses the CUDA engine (there is no fallback), whose collectives run inside
+    libtrueknn over NCCL — torch.distributed only carries the NCCL unique id and the optional gather=True."""
 
     def __init__(self, engine=None, device: int | None = None, group=None):
         self.group = group
@@ -40,28 +41,16 @@ class ShardedTrueKNN:
         return self
 
     def build_from_slices(self, local_points, n_total: int, device=None):
-        """Each rank holds only its contiguous 1/N slice of the cloud (host or device): upload the slice, assemble
-        the full cloud on every GPU with ONE all_gather over NVLink, then build the replicated LBVH.  Moves
-        n/N points over PCIe per rank instead of n (the only collective of the query-sharded variant, and it is
-        on the build path, not the search path)."""
-        if not torch.is_tensor(local_points):
-            local_points = torch.from_numpy(local_points)
-        if device is None:
-            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else local_points.device
-        loc = local_points.to(device, non_blocking=True).contiguous()
-        if self.world == 1:
-            full = loc
-        else:
-            per = (n_total + self.world - 1) // self.world          # slices are ceil(n/N) rows, the last one shorter
-            pad = torch.zeros((per, loc.shape[1]), dtype=loc.dtype, device=device)
-            pad[: loc.shape[0]] = loc
-            full = torch.empty((per * self.world, loc.shape[1]), dtype=loc.dtype, device=device)
-            dist.all_gather_into_tensor(full, pad, group=self.group)
-            full = full[:n_total].contiguous() if per * self.world != n_total else full
-        self._full = full
-        if full.is_cuda:
-            torch.cuda.current_stream(full.device).synchronize()  # the engine may run on a stream of its own
-        return self.build(full)
+        """Each rank holds only its contiguous ceil(n/N)-row slice of the cloud (host or device).  The library uploads
+        the slice, assembles the cloud on every GPU with ONE ncclAllGather over NVLink and builds the replicated LBVH
+        (tknn_build_replicated): n/N points cross PCIe per rank instead of n.  It is the only collective of the
+        query-sharded variant, and it is on the build path, not the search path."""
+        per = (n_total + self.world - 1) // self.world
+        if getattr(self.engine, "n_ranks", None) is None:
+            self.engine.comm_init_torch(self.group)
+        self.engine.build_replicated(local_points, min(n_total, per * self.rank), n_total)
+        self.n = int(n_total)
+        return self
 
     def search(self, k: int, start_radius: float = 0.0, gather: bool = False):
         """Local shard: (qid [m], idx [m, k], dist [m, k]).  gather=True: (idx [n, k], dist [n, k]) on every rank."""

@@ -140,8 +140,19 @@ class TrueKNN:
         if _is_tensor(like):
             import torch
 
-            return torch.empty((rows, k), dtype={np.int32: torch.int32, np.float32: torch.float32}[dtype], device=like.device)
+            out = torch.empty((rows, k), dtype={np.int32: torch.int32, np.float32: torch.float32}[dtype], device=like.device)
+            self._settle_outputs(out)
+            return out
         return np.empty((rows, k), dtype)
+
+    def _settle_outputs(self, t):
+        """The caching allocator may hand back a block that a kernel still pending on torch's current stream uses.
+        While the context runs on its OWN stream nothing orders that kernel before the engine's writes: settle torch's
+        stream first (a no-op cost when the context was given torch's stream with set_stream)."""
+        if self._own_stream and _is_tensor(t) and t.is_cuda:
+            import torch
+
+            torch.cuda.current_stream(t.device).synchronize()
 
     # ---- the path ----
     def build(self, points, dim: int | None = None):
@@ -247,6 +258,96 @@ class TrueKNN:
         self._check(self._L.tknn_merge_topk(self._h, self._in(idx_parts), self._in(d2_parts), parts, nq, k, _ptr(idx), _ptr(dist)))
         return idx, dist
 
+    # ---- multi-GPU, one rank per process (include/trueknn.h "multi-GPU" (b)) ----
+    @staticmethod
+    def unique_id() -> bytes:
+        """128 bytes from ncclGetUniqueId: rank 0 creates them, every rank passes them to comm_init."""
+        L = _lib.load()
+        buf = C.create_string_buffer(_lib.UNIQUE_ID_BYTES)
+        rc = L.tknn_comm_unique_id(buf)
+        if rc != _lib.OK:
+            raise TrueKNNError(rc, "tknn_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return buf.raw
+
+    def comm_init(self, n_ranks: int, rank: int, unique_id: bytes):
+        if len(unique_id) != _lib.UNIQUE_ID_BYTES:
+            raise ValueError("unique_id must be 128 bytes")
+        self._check(self._L.tknn_comm_init(self._h, int(n_ranks), int(rank), C.c_char_p(unique_id)))
+        self.rank, self.n_ranks = int(rank), int(n_ranks)
+        return self
+
+    def comm_init_torch(self, group=None):
+        """Communicator over the ranks of a torch.distributed group: the unique id travels through the group."""
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [self.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return self.comm_init(world, rank, box[0])
+
+    def dist_stats(self) -> dict:
+        s = _lib.DistStats()
+        self._check(self._L.tknn_get_dist_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def build_replicated(self, local_points, first: int, n_total: int, dim: int | None = None):
+        """TKNN_SHARD_QUERIES build: this rank's contiguous slice in, the replicated LBVH out (one ncclAllGather)."""
+        if not _is_tensor(local_points):
+            local_points = np.ascontiguousarray(local_points, dtype=np.float32)
+        _check_dtype(local_points, np.float32, "local_points")
+        stride = int(local_points.shape[1])
+        if dim is None:
+            dim = min(stride, 3)
+        self._check(self._L.tknn_build_replicated(self._h, self._in(local_points), int(local_points.shape[0]), int(first),
+                                                  int(n_total), int(dim), stride))
+        self.n = int(n_total)
+        self._like = local_points
+        return self
+
+    def partition_build(self, local_points, first_index: int, dim: int | None = None):
+        """TKNN_PARTITION_POINTS build: rows of global indices first_index.. in, one Morton range of the cloud owned."""
+        if not _is_tensor(local_points):
+            local_points = np.ascontiguousarray(local_points, dtype=np.float32)
+        _check_dtype(local_points, np.float32, "local_points")
+        stride = int(local_points.shape[1])
+        if dim is None:
+            dim = min(stride, 3)
+        self._check(self._L.tknn_partition_build(self._h, self._in(local_points), int(local_points.shape[0]), int(first_index),
+                                                 int(dim), stride))
+        self.n = int(self._L.tknn_partition_owned(self._h))
+        self._like = local_points
+        return self
+
+    def partition_owned(self) -> int:
+        return int(self._L.tknn_partition_owned(self._h))
+
+    def partition_search(self, k: int, start_radius: float = 0.0, out=None):
+        """Exact kNN of the owned points against the global cloud: (gid [m], idx [m,k] global ids, dist [m,k])."""
+        m = self.partition_owned()
+        if out is None:
+            if _is_tensor(self._like):
+                import torch
+
+                gid = torch.empty((m,), dtype=torch.int32, device=self._like.device)
+            else:
+                gid = np.empty((m,), np.int32)
+            idx = self._out(self._like, m, k, np.int32)
+            dist = self._out(self._like, m, k, np.float32)
+        else:
+            gid, idx, dist = out
+        got = C.c_uint64(0)
+        self._check(self._L.tknn_partition_search(self._h, int(k), C.c_float(start_radius), _ptr(gid), _ptr(idx), _ptr(dist),
+                                                  int(gid.shape[0]), C.byref(got)))
+        g = int(got.value)
+        return gid[:g], idx[:g], dist[:g]
+
+    def partition_verify(self, k: int, samples: int, gid, idx, dist):
+        """Distributed brute-force check of `samples` sampled rows per rank; returns GLOBAL (checked, bad)."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._L.tknn_partition_verify(self._h, int(k), int(samples), self._in(gid), self._in(idx), self._in(dist),
+                                                  int(gid.shape[0]), C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     # ---- introspection (tests / bench) ----
     def sort_pairs(self, keys, values):
         n = int(keys.shape[0])
@@ -305,6 +406,87 @@ class TrueKNN:
         return {"l2_gbs": l2.value, "hbm_read_gbs": hbm.value, "sm_count": sms.value, "l2_bytes": int(l2b.value)}
 
 
+class _RankView(TrueKNN):
+    """A rank's context inside a MultiTrueKNN (owned by it): statistics and options only."""
+
+    def __init__(self, L, handle):  # noqa: D401 — no tknn_create here
+        self._L, self._h, self._own_stream, self.n, self._like = L, handle, True, 0, None
+
+    def close(self):
+        self._h = None
+
+
+class MultiTrueKNN:
+    """All devices from ONE process (`tknn_create_multi`): the device-list form of the reference's context
+    (owlContextCreate(ids, n), owl/include/owl/owl_host.h:360).  Host arrays in, host arrays in file order out.
+
+    mode: "shard" (BVH replicated, queries sharded) or "partition" (points partitioned by Morton range).
+    Naming one device several times runs that many ranks on it (how the single-GPU tests exercise the paths)."""
+
+    MODES = {"shard": _lib.SHARD_QUERIES, "partition": _lib.PARTITION_POINTS}
+
+    def __init__(self, device_ids, mode: str = "shard", **options):
+        self._L = _lib.load()
+        ids = (C.c_int * len(device_ids))(*[int(d) for d in device_ids])
+        h = C.c_void_p()
+        rc = self._L.tknn_create_multi(ids, len(device_ids), self.MODES[mode], C.byref(h))
+        if rc != _lib.OK:
+            raise TrueKNNError(rc, f"tknn_create_multi({list(device_ids)}, {mode}) failed")
+        self._h, self.mode, self.n = h, mode, 0
+        for name, v in options.items():
+            self.set_option(name, v)
+
+    def _check(self, rc):
+        if rc != _lib.OK:
+            raise TrueKNNError(rc, self._L.tknn_multi_last_error(self._h).decode())
+
+    def set_option(self, name: str, value: int):
+        self._check(self._L.tknn_multi_set_option(self._h, TrueKNN._OPTS[name], int(value)))
+
+    @property
+    def n_ranks(self) -> int:
+        return int(self._L.tknn_multi_ranks(self._h))
+
+    def rank(self, r: int) -> TrueKNN:
+        return _RankView(self._L, C.c_void_p(self._L.tknn_multi_ctx(self._h, int(r))))
+
+    def build(self, points, dim: int | None = None):
+        points = np.ascontiguousarray(points, dtype=np.float32)
+        stride = int(points.shape[1])
+        if dim is None:
+            dim = min(stride, 3)
+        self._check(self._L.tknn_multi_build(self._h, _ptr(points), int(points.shape[0]), int(dim), stride))
+        self.n = int(points.shape[0])
+        return self
+
+    def search(self, k: int, start_radius: float = 0.0, out=None):
+        idx, dist = out if out is not None else (np.empty((self.n, k), np.int32), np.empty((self.n, k), np.float32))
+        self._check(self._L.tknn_multi_search(self._h, int(k), C.c_float(start_radius), _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+    def times(self) -> dict:
+        t = (C.c_float * 4)()
+        self._check(self._L.tknn_multi_get_times(self._h, t))
+        return {"build_ms": t[0], "search_ms": t[1], "exchange_ms": t[2], "d2h_ms": t[3]}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.tknn_multi_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # ------------------------------------------------------------------------------------------------
 # The sample's command line (hostCode.cpp:66-73) as a function.
 # ------------------------------------------------------------------------------------------------
@@ -355,12 +537,19 @@ def read_points_fast(path: str, n: int, dim: int) -> np.ndarray:
     """Same grammar as read_points, parsed in parallel by libtrueknn (tknn_read_points)."""
     L = _lib.load()
     cap = int(n) + 8
-    out = np.empty((cap, 3), np.float32)
     m = C.c_uint64(0)
-    rc = L.tknn_read_points(path.encode(), int(n), int(dim), C.c_void_p(out.ctypes.data), cap, C.byref(m))
-    if rc != _lib.OK:
-        raise ValueError(f"tknn_read_points({path!r}) failed with {_lib.ERROR_NAMES.get(rc, rc)}")
-    return np.ascontiguousarray(out[: int(m.value)])
+    for _ in range(2):
+        out = np.empty((cap, 3), np.float32)
+        rc = L.tknn_read_points(path.encode(), int(n), int(dim), C.c_void_p(out.ctypes.data), cap, C.byref(m))
+        if rc == _lib.OK:
+            return np.ascontiguousarray(out[: int(m.value)])
+        # The last line read is consumed whole (hostCode.cpp:92), so a file with many floats per line yields more
+        # than n rows: *n_out then names the row count needed — retry once with that capacity.
+        if rc == _lib.EINVAL and int(m.value) > cap:
+            cap = int(m.value)
+            continue
+        break
+    raise ValueError(f"tknn_read_points({path!r}) failed with {_lib.ERROR_NAMES.get(rc, rc)}")
 
 
 def write_neighbours(path: str, idx: np.ndarray, dist: np.ndarray, binary: bool = False):

@@ -41,6 +41,21 @@ class CpuEngine:
         self.n = self.x.shape[0]
         return self
 
+    n_ranks = 0  # "communicator" present: the stand-in talks through torch.distributed (gloo) itself
+
+    def build_replicated(self, local_points, first, n_total):
+        """Stand-in of tknn_build_replicated: padded all_gather of the slices over the default (gloo) group."""
+        import torch.distributed as dist
+
+        world = dist.get_world_size()
+        loc = torch.as_tensor(np.asarray(local_points, dtype=np.float32))
+        per = (n_total + world - 1) // world
+        pad = torch.zeros((per, loc.shape[1]), dtype=loc.dtype)
+        pad[: loc.shape[0]] = loc
+        full = torch.empty((per * world, loc.shape[1]), dtype=loc.dtype)
+        dist.all_gather_into_tensor(full, pad)
+        return self.build(full[:n_total].numpy())
+
     def search(self, k, start_radius=0.0):
         O.set_squared_output(bool(self.squared))
         try:

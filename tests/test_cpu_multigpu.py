@@ -1,6 +1,8 @@
-"""world_size > 1 on CPU (gloo): the host logic of the two multi-GPU drivers — shard bookkeeping,
-padding + all_gather, Morton-range redistribution, boundary-query routing, partial top-k merge —
-with a CPU stand-in engine answering the local searches through the oracle."""
+"""world_size > 1 on CPU (gloo): the host logic of the query-sharded driver (shard bookkeeping, slice upload +
+all_gather, padded gather of the results) and the protocol MODEL of the point-partitioned variant
+(tests/partition_model.py: Morton-range redistribution, boundary-query routing, merge on (d2, global index)) — the
+product runs that protocol inside libtrueknn over NCCL (csrc/dist.cu) and is tested on the GPU
+(tests/test_gpu_multi.py) — with a CPU stand-in engine answering the local searches through the oracle."""
 import os
 import socket
 import sys
@@ -58,11 +60,11 @@ def _worker(rank, world, port, mode, kind, n, k, out_dir):
             np.savez(os.path.join(out_dir, f"r{rank}.npz"), qid=np.asarray(qid), idx=np.asarray(idx), dist=np.asarray(dst),
                      gidx=gi.numpy(), gdist=gd.numpy())
         else:
-            from owlraytracing_b200.partitioned import PartitionedTrueKNN
+            from partition_model import PartitionModel
 
             # every rank starts with an arbitrary contiguous slice of the global index space
             lo, hi = n * rank // world, n * (rank + 1) // world
-            drv = PartitionedTrueKNN(engine=CpuEngine()).build(torch.from_numpy(x[lo:hi]), lo)
+            drv = PartitionModel(engine=CpuEngine()).build(torch.from_numpy(x[lo:hi]), lo)
             gid, idx, dst = drv.search(k)
             np.savez(os.path.join(out_dir, f"r{rank}.npz"), gid=gid.numpy(), idx=idx.numpy(), dist=dst.numpy(),
                      sent=drv.stats["boundary_sent"], owned=drv.stats["owned"])

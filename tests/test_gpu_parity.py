@@ -297,21 +297,6 @@ def test_merge_topk_and_morton_codes_match_the_cpu_stand_in(knn):
     assert np.allclose(gd.cpu().numpy(), ref_d.numpy(), rtol=1e-6, atol=0)
 
 
-def test_point_partitioned_driver_single_rank(knn, oracle):
-    """world_size 1 on the GPU: the partitioned driver degenerates to local search with global ids."""
-    import torch
-
-    from owlraytracing_b200.partitioned import PartitionedTrueKNN
-
-    x = datasets.uniform(30_000, seed=8)
-    drv = PartitionedTrueKNN(engine=knn).build(torch.from_numpy(x).cuda(), 1000)
-    gid, idx, dist = drv.search(10)
-    ref_i, ref_d = oracle.knn_kdtree(x, 10)
-    assert (gid.cpu().numpy() == np.arange(1000, 31_000)).all()
-    assert (idx.cpu().numpy() == ref_i + 1000).all()
-    assert np.allclose(dist.cpu().numpy(), ref_d, rtol=1e-6, atol=0)
-
-
 def test_cpp_cli_end_to_end(oracle, tmp_path):
     """tools/trueknn: the sample's six positional arguments (hostCode.cpp:66-73) through the C++ host."""
     import os

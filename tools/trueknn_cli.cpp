@@ -1,6 +1,12 @@
 // trueknn_cli.cpp — the sample's command line over libtrueknn (C++ host side of the drop-in).
 //
 //   trueknn <file> <n> <dim> <start radius> <k> <output file> [--neighbours <path>] [--device <d>] [--json]
+//           [--gpus <N> | --devices <a,b,...>] [--mode shard|partition]
+//
+// --gpus N (devices 0..N-1) or --devices (an explicit list; naming one device several times runs that many ranks on
+// it) drives all devices from this one process through tknn_create_multi: the device-list form of the reference's
+// owlContextCreate(ids, n) (owl/include/owl/owl_host.h:360; the sample itself passes one device, hostCode.cpp:141).
+// --mode shard: BVH replicated, queries sharded; --mode partition: points partitioned by Morton range.
 //
 // Mirrors samples/s01-trueknn/hostCode.cpp main() (argv contract :66-73): reads the first n points of
 // a text file (grammar :83-104, 2-D/3-D handling :114-124), builds the accel ("Build time",
@@ -22,18 +28,28 @@
 
 int main(int ac, char** av) {
   std::vector<std::string> pos;
-  std::string neigh_path;
+  std::string neigh_path, mode = "shard";
+  std::vector<int> devices;
   int device = 0;
   bool json = false;
   for (int i = 1; i < ac; ++i) {
     const std::string a = av[i];
     if (a == "--neighbours" || a == "--neighbors") { if (++i < ac) neigh_path = av[i]; }
     else if (a == "--device") { if (++i < ac) device = std::atoi(av[i]); }
+    else if (a == "--gpus") { if (++i < ac) { devices.clear(); for (int d = 0; d < std::atoi(av[i]); ++d) devices.push_back(d); } }
+    else if (a == "--devices") {
+      if (++i < ac) {
+        devices.clear();
+        for (const char* p = av[i]; *p;) { devices.push_back(std::atoi(p)); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
+      }
+    }
+    else if (a == "--mode") { if (++i < ac) mode = av[i]; }
     else if (a == "--json") json = true;
     else pos.push_back(a);
   }
-  if (pos.size() != 6) {
-    std::fprintf(stderr, "usage: %s <file> <n> <dim> <start radius> <k> <output file> [--neighbours <path>] [--device <d>] [--json]\n", av[0]);
+  if (pos.size() != 6 || (mode != "shard" && mode != "partition")) {
+    std::fprintf(stderr, "usage: %s <file> <n> <dim> <start radius> <k> <output file> [--neighbours <path>] [--device <d>] [--json]\n"
+                         "          [--gpus <N> | --devices <a,b,...>] [--mode shard|partition]\n", av[0]);
     return 64;
   }
   const std::string path = pos[0], outfile = pos[5];
@@ -47,12 +63,63 @@ int main(int ac, char** av) {
   if (n < 0) { std::fprintf(stderr, "number of points must be >= 0\n"); return 65; }
   std::vector<float> flat((size_t)(n + 8) * 3);
   uint64_t np = 0;
-  if (tknn_read_points(path.c_str(), (uint64_t)n, dim, flat.data(), (uint64_t)n + 8, &np) != TKNN_OK) {
+  int rrc = tknn_read_points(path.c_str(), (uint64_t)n, dim, flat.data(), (uint64_t)n + 8, &np);
+  if (rrc == TKNN_EINVAL && np > (uint64_t)n + 8) {  // several points per line: the last line read is consumed whole
+    const uint64_t cap = np;
+    flat.resize((size_t)cap * 3);
+    rrc = tknn_read_points(path.c_str(), (uint64_t)n, dim, flat.data(), cap, &np);
+  }
+  if (rrc != TKNN_OK) {
     std::fprintf(stderr, "cannot read %s as %d-D points (unreadable, or the float count is not a multiple of dim — "
                          "the reference throws std::out_of_range there)\n", path.c_str(), dim);
     return 66;
   }
   std::cout << " num spheres: " << np << "\n";
+
+  if (!devices.empty()) {
+    // ---- all devices from this process (tknn_create_multi) ----
+    tknn_multi* mg = nullptr;
+    int mrc = tknn_create_multi(devices.data(), (int)devices.size(), mode == "shard" ? TKNN_SHARD_QUERIES : TKNN_PARTITION_POINTS, &mg);
+    if (mrc != TKNN_OK) { std::fprintf(stderr, "tknn_create_multi failed (%d): CUDA sm_100 devices and NCCL are required\n", mrc); return 70; }
+    auto m0 = std::chrono::steady_clock::now();
+    mrc = tknn_multi_build(mg, flat.data(), np, 3, 3);
+    auto m1 = std::chrono::steady_clock::now();
+    if (mrc != TKNN_OK) { std::fprintf(stderr, "tknn_multi_build: %s\n", tknn_multi_last_error(mg)); tknn_multi_destroy(mg); return 71; }
+    const double mbuild_s = std::chrono::duration<double>(m1 - m0).count();
+    std::cout << "Build time: " << mbuild_s << '\n';
+    std::vector<int32_t> midx((size_t)np * k);
+    std::vector<float> mdist((size_t)np * k);
+    auto m2 = std::chrono::steady_clock::now();
+    mrc = tknn_multi_search(mg, k, radius, midx.data(), mdist.data());
+    auto m3 = std::chrono::steady_clock::now();
+    if (mrc != TKNN_OK) { std::fprintf(stderr, "tknn_multi_search: %s\n", tknn_multi_last_error(mg)); tknn_multi_destroy(mg); return 72; }
+    const double mknn_s = std::chrono::duration<double>(m3 - m2).count();
+    for (int r = 0; r < tknn_multi_ranks(mg); ++r) {
+      tknn_stats st;
+      tknn_get_stats(tknn_multi_ctx(mg, r), &st);
+      std::cout << "GPU " << devices[r] << " (rank " << r << "): " << st.n_queries << " queries, " << st.rounds << " rounds, start radius "
+                << st.start_radius << ", search " << st.search_ms / 1000.0 << " seconds\n";
+    }
+    std::cout << "True KNN time: " << mknn_s << " seconds." << std::endl;
+    std::cout << "Total time: " << mbuild_s + mknn_s << '\n';
+    std::ofstream mout(outfile, std::ios::app);
+    if (!mout.is_open()) { std::perror("Error open"); tknn_multi_destroy(mg); return 73; }
+    mout << mbuild_s + mknn_s << std::endl;
+    if (!neigh_path.empty() && tknn_write_neighbours(neigh_path.c_str(), midx.data(), mdist.data(), np, k, 0) != TKNN_OK) {
+      std::perror("Error open");
+      tknn_multi_destroy(mg);
+      return 73;
+    }
+    if (json) {
+      float tm[4];
+      tknn_multi_get_times(mg, tm);
+      std::printf("{\"n\": %llu, \"k\": %d, \"gpus\": %d, \"mode\": \"%s\", \"build_ms\": %.4f, \"search_ms\": %.4f, "
+                  "\"exchange_ms\": %.4f, \"d2h_ms\": %.4f}\n",
+                  (unsigned long long)np, k, (int)devices.size(), mode.c_str(), tm[0], tm[1], tm[2], tm[3]);
+    }
+    tknn_multi_destroy(mg);
+    return 0;
+  }
 
   tknn_ctx* ctx = nullptr;
   int rc = tknn_create(device, &ctx);
