@@ -332,6 +332,11 @@ TKNN_API int tknn_write_neighbours(const char* path, const int32_t* idx, const f
  * bandwidth (GB/s) from a short read loop over an L2-resident / HBM-sized buffer. */
 TKNN_API int tknn_measure_bandwidth(tknn_ctx* ctx, double* l2_gbs, double* hbm_gbs, int* sm_count, uint64_t* l2_bytes);
 
+/* Measured aggregate shared-memory bandwidth (GB/s of bytes delivered to lanes): conflict-free LDS.128 — the
+ * 128 B/clk/SM crossbar — and warp-broadcast LDS.128, the access pattern of the traversal kernel's leaf filter.
+ * The traversal kernel is bound by this data path (and by issue slots), not by HBM: bench.py's roofline uses it. */
+TKNN_API int tknn_measure_smem_bandwidth(tknn_ctx* ctx, double* conflict_free_gbs, double* broadcast_gbs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,6 +100,15 @@ TKO_INLINE void tko_list_emit(const uint64_t* list, int cnt, int k, int32_t* idx
   }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm of bench.py must still use every core */
+TKO_API void tko_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 TKO_API int tko_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
@@ -328,6 +337,36 @@ TKO_API int tko_kdtree_knn(const tko_kdtree* t, const float* q, int64_t nq, cons
     }
     free(list);
   }
+  return 0;
+}
+
+/* Queries = the points at TREE positions pos[0..nq) (self excluded by index), rows in the order of pos.  Runs of
+ * consecutive positions are neighbours in space, which is the order the GPU arm processes its queries in (Morton
+ * order): the fair form of a sampled CPU baseline (bench.py) — index-sorted samples are cache-hostile. */
+TKO_CLONES
+TKO_API int tko_kdtree_knn_positions(const tko_kdtree* t, const int64_t* pos, int64_t nq, int k, float radius2,
+                                     int32_t* idx_out, float* dist_out) {
+  if (!t || !pos || k <= 0) return 1;
+#pragma omp parallel
+  {
+    uint64_t* list = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)k);
+#pragma omp for schedule(dynamic, 256)
+    for (int64_t i = 0; i < nq; ++i) {
+      const int64_t p = pos[i];
+      int cnt = 0;
+      if (p >= 0 && p < t->n)
+        tko_kd_query(t, t->pts[3 * p], t->pts[3 * p + 1], t->pts[3 * p + 2], t->ids[p], k, radius2, list, &cnt);
+      tko_list_emit(list, cnt, k, idx_out + i * k, dist_out + i * k);
+    }
+    free(list);
+  }
+  return 0;
+}
+
+/* original index of the point at each tree position (to check sampled answers) */
+TKO_API int tko_kdtree_ids(const tko_kdtree* t, const int64_t* pos, int64_t nq, int32_t* ids_out) {
+  if (!t || !pos) return 1;
+  for (int64_t i = 0; i < nq; ++i) ids_out[i] = (pos[i] >= 0 && pos[i] < t->n) ? t->ids[pos[i]] : -1;
   return 0;
 }
 

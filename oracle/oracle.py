@@ -44,6 +44,9 @@ def lib() -> C.CDLL:
         L.tko_kdtree_build.argtypes = [f32p, C.c_int64, C.c_int]
         L.tko_kdtree_free.argtypes = [C.c_void_p]
         L.tko_kdtree_knn.argtypes = [C.c_void_p, f32p, C.c_int64, i32p, C.c_int, C.c_float, i32p, f32p]
+        L.tko_kdtree_knn_positions.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int64, C.c_int, C.c_float, i32p, f32p]
+        L.tko_kdtree_ids.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int64, i32p]
+        L.tko_set_num_threads.argtypes = [C.c_int]
         L.tko_range_count.argtypes = [f32p, C.c_int64, C.c_float, u32p]
         L.tko_reference_trueknn.argtypes = [f32p, C.c_int64, C.c_int, C.c_float, C.c_int, i32p, f32p,
                                             C.POINTER(C.c_int), C.POINTER(C.c_float)]
@@ -63,6 +66,11 @@ def _p(a, t):
 
 def num_threads() -> int:
     return int(lib().tko_num_threads())
+
+
+def set_num_threads(n: int):
+    """Override OMP_NUM_THREADS (torchrun exports 1 to its workers)."""
+    lib().tko_set_num_threads(int(n))
 
 
 def dist2(q, p) -> np.float32:
@@ -136,6 +144,19 @@ class KdTree:
                                   _p(idx, C.c_int32), _p(dist, C.c_float))
         assert rc == 0
         return idx, dist
+
+    def query_positions(self, pos, k, radius2=np.inf):
+        """Queries = the points at tree positions `pos` (runs of consecutive positions are spatially coherent).
+        Returns (ids [m] original indices of the queries, idx [m,k], dist [m,k])."""
+        pos = np.ascontiguousarray(pos, dtype=np.int64)
+        m = pos.shape[0]
+        ids = np.empty(m, np.int32)
+        idx = np.empty((m, k), np.int32)
+        dist = np.empty((m, k), np.float32)
+        pp = pos.ctypes.data_as(C.POINTER(C.c_int64))
+        assert lib().tko_kdtree_ids(self._h, pp, m, _p(ids, C.c_int32)) == 0
+        assert lib().tko_kdtree_knn_positions(self._h, pp, m, k, C.c_float(radius2), _p(idx, C.c_int32), _p(dist, C.c_float)) == 0
+        return ids, idx, dist
 
     def close(self):
         if self._h:

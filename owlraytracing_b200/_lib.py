@@ -97,7 +97,7 @@ EXPORTS = [
     "tknn_comm_unique_id", "tknn_comm_init", "tknn_get_dist_stats", "tknn_build_replicated", "tknn_partition_build",
     "tknn_partition_owned", "tknn_partition_search", "tknn_partition_verify", "tknn_create_multi", "tknn_multi_destroy",
     "tknn_multi_set_option", "tknn_multi_build", "tknn_multi_search", "tknn_multi_ranks", "tknn_multi_ctx",
-    "tknn_multi_last_error", "tknn_multi_get_times",
+    "tknn_multi_last_error", "tknn_multi_get_times", "tknn_measure_smem_bandwidth",
 ]
 
 _lib = None
@@ -141,6 +141,7 @@ def load() -> C.CDLL:
     L.tknn_write_neighbours.argtypes = [C.c_char_p, vp, vp, u64, C.c_int, C.c_int]
     L.tknn_measure_bandwidth.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int),
                                          C.POINTER(u64)]
+    L.tknn_measure_smem_bandwidth.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.tknn_comm_unique_id.argtypes = [vp]
     L.tknn_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.tknn_get_dist_stats.argtypes = [vp, C.POINTER(DistStats)]

@@ -1386,4 +1386,33 @@ int tknn_measure_bandwidth(tknn_ctx* c, double* l2_gbs, double* hbm_gbs, int* sm
   return TKNN_OK;
 }
 
+// Aggregate shared-memory bandwidth in GB/s of bytes delivered to lanes: conflict-free LDS.128 (the 128 B/clk/SM
+// crossbar) and warp-broadcast LDS.128 (the traversal kernel's leaf filter).  Best of 5 runs of ~1 ms each.
+int tknn_measure_smem_bandwidth(tknn_ctx* c, double* conflict_free_gbs, double* broadcast_gbs) {
+  TK_TRY(check_ctx(c));
+  ScopedDevice sd(c->device);
+  cudaStream_t st = c->stream;
+  uint32_t* sink = c->scalars.as<uint32_t>() + SC_WORDS - 1;
+  const unsigned grid = (unsigned)c->sm_count * 8;
+  const int iters = 2048;
+  for (int mode = 0; mode < 2; ++mode) {
+    double best = 0;
+    brute::smem_probe_kernel<<<grid, 256, 0, st>>>(64, mode, sink);  // warm
+    for (int rep = 0; rep < 5; ++rep) {
+      float ms = 0.f;
+      TK_CUDA(c, cudaEventRecord(c->ev[0], st));
+      brute::smem_probe_kernel<<<grid, 256, 0, st>>>(iters, mode, sink);
+      TK_CUDA(c, cudaEventRecord(c->ev[1], st));
+      TK_CUDA(c, cudaEventSynchronize(c->ev[1]));
+      TK_CUDA(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+      const double gbs = (double)grid * 256 * iters * 8 * 16 / (ms * 1e-3) / 1e9;
+      if (gbs > best) best = gbs;
+    }
+    if (mode == 0 && conflict_free_gbs) *conflict_free_gbs = best;
+    if (mode == 1 && broadcast_gbs) *broadcast_gbs = best;
+  }
+  TK_CUDA(c, cudaGetLastError());
+  return TKNN_OK;
+}
+
 }  // extern "C"

@@ -405,6 +405,11 @@ class TrueKNN:
         self._check(self._L.tknn_measure_bandwidth(self._h, C.byref(l2), C.byref(hbm), C.byref(sms), C.byref(l2b)))
         return {"l2_gbs": l2.value, "hbm_read_gbs": hbm.value, "sm_count": sms.value, "l2_bytes": int(l2b.value)}
 
+    def measure_smem_bandwidth(self) -> dict:
+        a, b = C.c_double(0), C.c_double(0)
+        self._check(self._L.tknn_measure_smem_bandwidth(self._h, C.byref(a), C.byref(b)))
+        return {"smem_conflict_free_gbs": a.value, "smem_broadcast_gbs": b.value}
+
 
 class _RankView(TrueKNN):
     """A rank's context inside a MultiTrueKNN (owned by it): statistics and options only."""

@@ -1,6 +1,6 @@
 // trueknn_cli.cpp — the sample's command line over libtrueknn (C++ host side of the drop-in).
 //
-//   trueknn <file> <n> <dim> <start radius> <k> <output file> [--neighbours <path>] [--device <d>] [--json]
+//   trueknn <file> <n> <dim> <start radius> <k> <output file> [--neighbours <path> [--binary]] [--device <d>] [--json]
 //           [--gpus <N> | --devices <a,b,...>] [--mode shard|partition]
 //
 // --gpus N (devices 0..N-1) or --devices (an explicit list; naming one device several times runs that many ranks on
@@ -31,7 +31,7 @@ int main(int ac, char** av) {
   std::string neigh_path, mode = "shard";
   std::vector<int> devices;
   int device = 0;
-  bool json = false;
+  bool json = false, binary = false;
   for (int i = 1; i < ac; ++i) {
     const std::string a = av[i];
     if (a == "--neighbours" || a == "--neighbors") { if (++i < ac) neigh_path = av[i]; }
@@ -45,6 +45,7 @@ int main(int ac, char** av) {
     }
     else if (a == "--mode") { if (++i < ac) mode = av[i]; }
     else if (a == "--json") json = true;
+    else if (a == "--binary") binary = true;  // --neighbours as raw arrays: <path>.idx.i32 / <path>.dist.f32
     else pos.push_back(a);
   }
   if (pos.size() != 6 || (mode != "shard" && mode != "partition")) {
@@ -105,7 +106,7 @@ int main(int ac, char** av) {
     std::ofstream mout(outfile, std::ios::app);
     if (!mout.is_open()) { std::perror("Error open"); tknn_multi_destroy(mg); return 73; }
     mout << mbuild_s + mknn_s << std::endl;
-    if (!neigh_path.empty() && tknn_write_neighbours(neigh_path.c_str(), midx.data(), mdist.data(), np, k, 0) != TKNN_OK) {
+    if (!neigh_path.empty() && tknn_write_neighbours(neigh_path.c_str(), midx.data(), mdist.data(), np, k, binary ? 1 : 0) != TKNN_OK) {
       std::perror("Error open");
       tknn_multi_destroy(mg);
       return 73;
@@ -155,7 +156,7 @@ int main(int ac, char** av) {
   out << tot << std::endl;
 
   if (!neigh_path.empty()) {
-    if (tknn_write_neighbours(neigh_path.c_str(), idx.data(), dist.data(), np, k, 0) != TKNN_OK) {
+    if (tknn_write_neighbours(neigh_path.c_str(), idx.data(), dist.data(), np, k, binary ? 1 : 0) != TKNN_OK) {
       std::perror("Error open");
       tknn_destroy(ctx);
       return 73;
