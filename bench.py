@@ -338,6 +338,11 @@ def run_gpu(args):
             dist.all_reduce(tm, op=dist.ReduceOp.SUM)
         return [int(v) for v in tm.tolist()]
 
+    # ONE JSON line on stdout: whatever libraries print there (NCCL announces its version on stdout) goes to stderr
+    json_fd = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
+
     wl = resolve_workload(args)
     cfg = WORKLOADS[wl]
     k = cfg["k"]
@@ -526,7 +531,8 @@ def run_gpu(args):
                                                         "search_total_ms", "boundary_sent", "boundary_received",
                                                         "bytes_sent_search")}
             line["partition"]["bytes_sent_build"] = dstats_build["bytes_sent_build"]
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     t.close()
     if world > 1:
         dist.destroy_process_group()

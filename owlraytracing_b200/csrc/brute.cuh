@@ -252,17 +252,21 @@ static __global__ void __launch_bounds__(256) read_probe_kernel(const uint4* __r
 // warp read 32 consecutive float4 (conflict-free, 512 B per instruction = 4 wavefronts of 128 B); broadcast = 1: all
 // lanes of a warp read ONE float4 (the access pattern of the traversal kernel's leaf filter: one wavefront per
 // instruction).  Bytes DELIVERED to lanes = threads x iters x 8 x 16 in both cases.
-static __global__ void __launch_bounds__(256) smem_probe_kernel(int iters, int broadcast, uint32_t* __restrict__ sink) {
+static __global__ void __launch_bounds__(256) smem_probe_kernel(int iters, int broadcast, int stride, uint32_t* __restrict__ sink) {
   __shared__ float4 s[1024];
   for (int i = threadIdx.x; i < 1024; i += 256) s[i] = make_float4((float)i, 1.0f, 2.0f, 3.0f);
   __syncthreads();
   uint32_t ax = 0, ay = 0, az = 0, aw = 0;
   const int base = broadcast ? (int)(threadIdx.x >> 5) * 37 : (int)threadIdx.x;
+  const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(s);
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const float4 v = s[(base + it * 8 * 32 + u * 32) & 1023];
-      ax ^= __float_as_uint(v.x); ay ^= __float_as_uint(v.y); az ^= __float_as_uint(v.z); aw ^= __float_as_uint(v.w);
+      // asm volatile: every load is issued (the compiler may neither hoist nor merge them); `stride` is a run-time value
+      const uint32_t addr = s0 + 16u * (uint32_t)((base + it * stride + u * 32) & 1023);
+      uint32_t x, y, z, w;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(addr));
+      ax ^= x; ay ^= y; az ^= z; aw ^= w;
     }
   }
   if ((ax ^ ay ^ az ^ aw) == 0x12345678u) *sink = ax;

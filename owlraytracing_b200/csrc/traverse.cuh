@@ -160,40 +160,84 @@ __device__ __forceinline__ void pheap_sift_root(uint64_t* A, int size, uint64_t 
 }
 #undef TKNN_MAX2
 
-// ---- bounded ASCENDING list of u64 keys in shared memory (slot s of lane l at L[s * 32 + l]) ----
+// Insert iterations with at most this many lanes holding a candidate are done cooperatively (coop_insert): a
+// private insert iteration costs ~95 warp instructions whatever the number of lanes in it, a cooperative insert ~30
+// per candidate.  -DTKNN_COOP_MAX_LANES=0 switches the cooperative path off.
+// MEASURED AND REJECTED (profiles/r2_ab_coop_cfg2.jsonl, cfg2 round 1): off 7.48 ms, <= 2 lanes 7.98, <= 3 lanes 8.36,
+// <= 5 lanes 9.25, <= 8 lanes 10.57 ms.  A cooperative insert is a chain of dependent warp-wide steps (7 shuffles, two
+// shared-memory round trips, a ballot) with no overlap between candidates, while the private path lets every lane
+// with a candidate walk its own list at once; the 95-instruction average of a private iteration is dominated by the
+// many-lane iterations, a one-lane iteration is far cheaper than that.  Kept behind the macro (default 0 = off).
+#ifndef TKNN_COOP_MAX_LANES
+#define TKNN_COOP_MAX_LANES 0
+#endif
+constexpr int COOP_MAX_LANES = TKNN_COOP_MAX_LANES;
+
+// ---- bounded ASCENDING list of u64 keys in shared memory (slot s of lane l at L[s * S + l]) ----
 // Candidates arrive roughly nearest-first, so a new key usually lands near the tail: the backward
 // shift is short, and the list needs no heap-sort at emit time.  Precondition: cnt < k or key < L[k-1].
 // L points at a SENTINEL slot holding 0 (<= every key); entries live in slots 1..k.  The sentinel ends
 // the backward walk without a bounds test, so the loop unrolls to 5 instructions per step.
+// S = slot stride in keys: 32 (one 256-byte row per slot), or KLS = 33 in the cooperative kernel, where a row is
+// padded by one key so that the k slots of ONE lane fall into distinct banks (2 s mod 32): the warp can then read or
+// shift a single query's whole list in one conflict-free access (coop_insert below), while the per-lane accesses
+// (32 consecutive keys of one slot) stay conflict-free too.
+constexpr int KLS = COOP_MAX_LANES > 0 ? 33 : 32;
+
+template <int S = 32>
 __device__ __forceinline__ void list_insert(uint64_t* L, int& cnt, int k, uint64_t key) {
-  uint64_t* p = L + (cnt < k ? cnt + 1 : k) * 32;  // the slot being filled
+  uint64_t* p = L + (cnt < k ? cnt + 1 : k) * S;  // the slot being filled
   if (cnt < k) ++cnt;
   for (;;) {
     // four independent loads in flight: one shared-memory latency per four steps.  Slots below the
     // sentinel (at most three) are never used: the walk stops at the sentinel; they lie inside this
     // warp's own staging area, so the reads are in bounds.
-    const uint64_t a = *(p - 32), b = *(p - 64), c = *(p - 96), d = *(p - 128);
+    const uint64_t a = *(p - S), b = *(p - 2 * S), c = *(p - 3 * S), d = *(p - 4 * S);
     if (a <= key) { *p = key; return; }
     *p = a;
-    if (b <= key) { *(p - 32) = key; return; }
-    *(p - 32) = b;
-    if (c <= key) { *(p - 64) = key; return; }
-    *(p - 64) = c;
-    if (d <= key) { *(p - 96) = key; return; }
-    *(p - 96) = d;
-    p -= 128;
+    if (b <= key) { *(p - S) = key; return; }
+    *(p - S) = b;
+    if (c <= key) { *(p - 2 * S) = key; return; }
+    *(p - 2 * S) = c;
+    if (d <= key) { *(p - 3 * S) = key; return; }
+    *(p - 3 * S) = d;
+    p -= 4 * S;
   }
+}
+
+// ---- cooperative insert: the whole warp works on ONE query's list ------------------------------------------
+// Most insert iterations of the dense kernel have one or two lanes with a candidate (a leaf away from a query's own
+// leaf improves few of the 32 lists), and a lane's private shift loop then runs at 1-2 of 32 lanes: 36 % of all warp
+// instructions on cfg2 (profiles/r2_traverse_cfg2_v9_regions.txt).  Here lane i owns rank i of the list of lane
+// `src`: one conflict-free load of the list (stride KLS), one ballot for the position, one predicated store for the
+// shift, one for the key — the same ~25 instructions whatever the shift length.  All arguments are warp-uniform;
+// Ls = sentinel slot of src's list.  Returns the updated count; `worst` receives the rank-(k-1) key once the list is
+// full.  Keys are distinct (distinct indices), the list ascends, k <= LIST_MAX_K < 32.
+__device__ __forceinline__ int coop_insert(uint64_t* Ls, int cnt, int k, uint64_t key, int lane, uint64_t& worst, bool& inserted) {
+  const uint64_t e = lane < cnt ? Ls[(lane + 1) * KLS] : ~0ull;  // rank `lane` (ranks past the count compare high)
+  const int pos = __popc(__ballot_sync(FULL_MASK, e < key));     // entries smaller than the key = its rank
+  inserted = pos < k;
+  if (!inserted) return cnt;                                     // a full list whose worst entry beats the key
+  const int ncnt = cnt < k ? cnt + 1 : k;
+  if (lane >= pos && lane + 1 < ncnt) Ls[(lane + 2) * KLS] = e;  // ranks pos .. ncnt-2 move up by one (the last one falls off)
+  if (lane == pos) Ls[(pos + 1) * KLS] = key;
+  if (ncnt == k) {                                               // new worst: the key itself, or old rank k-2 moved up
+    const uint64_t up = __shfl_sync(FULL_MASK, e, k >= 2 ? k - 2 : 0);
+    worst = pos == k - 1 ? key : up;
+  }
+  return ncnt;
 }
 
 // k-list policy: ascending list for small k (short shifts, no sort at emit), 4-ary max-heap above
 // (O(log4 k) per insert; heap-sorted at emit).  Warp-uniform choice.
 constexpr int LIST_MAX_K = 24;
 
-// H = sentinel slot of the lane's region; the heap (large k) uses slots 1..k as its 0-based array
-__device__ __forceinline__ uint64_t kl_worst(const uint64_t* H, int k, bool heap) { return heap ? H[32] : H[k * 32]; }
+// H = sentinel slot of the lane's region; the heap (large k) uses slots 1..k as its 0-based array (stride 32 always)
+template <int S = 32>
+__device__ __forceinline__ uint64_t kl_worst(const uint64_t* H, int k, bool heap) { return heap ? H[32] : H[k * S]; }
 
 // PADDED: the padded D-ary heap of the cooperative kernel (pheap_*)
-template <bool PADDED = false>
+template <bool PADDED = false, int S = 32>
 __device__ __forceinline__ void kl_insert(uint64_t* H, int& cnt, int k, uint64_t key, bool heap) {
   if (heap) {
     if (PADDED) {
@@ -204,12 +248,12 @@ __device__ __forceinline__ void kl_insert(uint64_t* H, int& cnt, int k, uint64_t
       else heap_sift_root(H + 32, k, key);
     }
   } else {
-    list_insert(H, cnt, k, key);
+    list_insert<S>(H, cnt, k, key);
   }
 }
 
 // writes the k-list ascending to (io, dd); destroys the heap (PADDED: leaves it all zero)
-template <bool PADDED = false>
+template <bool PADDED = false, int S = 32>
 __device__ __forceinline__ void kl_emit(uint64_t* H, int cnt, int k, bool heap, bool squared, int32_t* io, float* dd) {
   for (int i = k - 1; i >= cnt; --i) { io[i] = -1; dd[i] = FLT_MAX; }
   if (heap) {
@@ -232,7 +276,7 @@ __device__ __forceinline__ void kl_emit(uint64_t* H, int cnt, int k, bool heap, 
     }
   } else {
     for (int i = 0; i < cnt; ++i) {
-      const uint64_t e = H[(i + 1) * 32];
+      const uint64_t e = H[(i + 1) * S];
       io[i] = key_idx(e);
       dd[i] = squared ? key_d2(e) : __fsqrt_rn(key_d2(e));
     }
@@ -242,8 +286,14 @@ __device__ __forceinline__ void kl_emit(uint64_t* H, int cnt, int k, bool heap, 
 // k-list slots per lane in the cooperative kernel: sentinel + k entries, + heap_pads(k) zero slots behind a heap
 __host__ __device__ inline int klist_slots(int k) { return k > LIST_MAX_K ? k + 1 + heap_pads(k) : k + 1; }
 
+// bytes of the 32 k-lists of a warp: rows of KLS keys for the ascending lists, of 32 keys for the heaps; a multiple of 16
+__host__ __device__ inline size_t klist_bytes(int k) {
+  const size_t b = (size_t)klist_slots(k) * (k > LIST_MAX_K ? 32 : KLS) * sizeof(uint64_t);
+  return (b + 15) / 16 * 16;
+}
+
 __host__ __device__ inline size_t smem_per_warp(int k) {
-  return (size_t)klist_slots(k) * 32 * sizeof(uint64_t) + 2 * MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int);
+  return klist_bytes(k) + 2 * MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int);
 }
 
 // ---- index-aware pruning of exact ties ----------------------------------------------------------
@@ -257,13 +307,13 @@ __host__ __device__ inline size_t smem_per_warp(int k) {
 // test applies to every exact tie, not only to bound == 0.  It lives in its own kernel variant (VARIANT 2),
 // selected only when the build saw a leaf of coincident points: compiled into the default variant it cost
 // 9 % on tie-free data (8.45 -> 9.2 ms on cfg2).
-template <int MODE>
+template <int MODE, int S>
 __device__ __forceinline__ bool child_wanted(float dc, float bound, int cnt, int k, const uint64_t* H, bool heap,
                                              int child_min_idx) {
   if (!__any_sync(FULL_MASK, dc <= bound)) return false;
   if (MODE != MODE_KNN) return true;
   if (__any_sync(FULL_MASK, dc < bound)) return true;
-  const bool tie_can_win = (dc == bound) && (cnt < k || child_min_idx < key_idx(kl_worst(H, k, heap)));
+  const bool tie_can_win = (dc == bound) && (cnt < k || child_min_idx < key_idx(kl_worst<S>(H, k, heap)));
   return __any_sync(FULL_MASK, tie_can_win);
 }
 
@@ -333,10 +383,11 @@ static __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
   unsigned char* wbase = smem + (size_t)warp * smem_per_warp(MODE == MODE_KNN ? k : 0);
   float4* stage = reinterpret_cast<float4*>(wbase);
   int* stack = reinterpret_cast<int*>(wbase + MAX_LEAF * sizeof(float4));
+  constexpr int S = HEAP ? 32 : KLS;  // slot stride of the k-lists (keys)
   uint64_t* H = reinterpret_cast<uint64_t*>(wbase + MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int)) + lane;
   // second staging array (relative coordinates + squared norm) for the pre-filter, behind the k-list
   float4* stage2 = reinterpret_cast<float4*>(wbase + MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int) +
-                                             (size_t)klist_slots(k) * 32 * sizeof(uint64_t));
+                                             klist_bytes(MODE == MODE_KNN ? k : 0));
   float* soa = reinterpret_cast<float*>(stage2);  // exact filter: the leaf's x[32] | y[32] | z[32] (same region)
 
   unsigned long long c_nodes = 0, c_tests = 0, c_ins = 0, c_wnodes = 0, c_wleaves = 0, c_wpts = 0, c_viol = 0;
@@ -399,7 +450,7 @@ static __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
           if (!__any_sync(FULL_MASK, dc <= bound)) continue;
           if (TIES && !__any_sync(FULL_MASK, dc < bound)) {  // only exact ties: can any of them win?
             const int2 mi = __ldg(&P.node_min_idx[node]);
-            if (!child_wanted<MODE>(dc, bound, cnt, k, H, heap, second ? mi.y : mi.x)) continue;
+            if (!child_wanted<MODE, S>(dc, bound, cnt, k, H, heap, second ? mi.y : mi.x)) continue;
           }
           const int start = second ? ref1 : ref0;
           float cx = 0.f, cy = 0.f, cz = 0.f;
@@ -465,7 +516,37 @@ static __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
                 mask |= filter4(soa, j0, qx2, qy2, qz2, bound) << j0;
             }
             // insert: only lanes with survivors do work; the bound tightens as they go
-            while (__any_sync(FULL_MASK, mask != 0u)) {
+            for (;;) {
+              unsigned pend = __ballot_sync(FULL_MASK, mask != 0u);
+              if (pend == 0u) break;
+              if (!HEAP && COOP_MAX_LANES > 0 && __popc(pend) <= COOP_MAX_LANES) {
+                // Few lanes hold candidates: the WARP inserts them, one (query, candidate) at a time (coop_insert).
+                // Nothing but `pend` lives across iterations: the owner lane keeps its own cnt / bound / mask.
+                __syncwarp();
+                do {
+                  const int src = __ffs(pend) - 1;
+                  const uint32_t smask = __shfl_sync(FULL_MASK, mask, src);
+                  const int j = __ffs(smask) - 1;
+                  if (lane == src) mask &= mask - 1u;
+                  if ((smask & (smask - 1u)) == 0u) pend &= pend - 1u;  // that was src's last candidate
+                  const float4 p = stage[j];
+                  const float d = dist2(__shfl_sync(FULL_MASK, q.x, src), __shfl_sync(FULL_MASK, q.y, src),
+                                        __shfl_sync(FULL_MASK, q.z, src), p.x, p.y, p.z);
+                  const int pid = __float_as_int(p.w);
+                  if (pid != __shfl_sync(FULL_MASK, self, src) && d <= __shfl_sync(FULL_MASK, bound, src)) {
+                    uint64_t worst = 0;
+                    bool ins;
+                    const int ncnt = coop_insert(H - lane + src, __shfl_sync(FULL_MASK, cnt, src), k, make_key(d, pid), lane, worst, ins);
+                    if (ins && lane == src) {
+                      cnt = ncnt;
+                      if (ncnt == k) bound = key_d2(worst);
+                      if (COUNT) c_ins += 1;
+                    }
+                    __syncwarp();
+                  }
+                } while (pend);
+                break;
+              }
               if (mask) {
                 const int j = __ffs(mask) - 1;
                 mask &= mask - 1u;
@@ -474,9 +555,9 @@ static __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
                 const int pid = __float_as_int(p.w);
                 if (pid != self && d <= bound) {
                   const uint64_t key = make_key(d, pid);
-                  if (cnt < k || key < kl_worst(H, k, heap)) {
-                    kl_insert<true>(H, cnt, k, key, heap);
-                    if (cnt == k) bound = key_d2(kl_worst(H, k, heap));
+                  if (cnt < k || key < kl_worst<S>(H, k, heap)) {
+                    kl_insert<true, S>(H, cnt, k, key, heap);
+                    if (cnt == k) bound = key_d2(kl_worst<S>(H, k, heap));
                     if (COUNT) c_ins += 1;
                   }
                 }
@@ -492,8 +573,8 @@ static __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
       bool w1 = (cnt1 == 0) && __any_sync(FULL_MASK, d1 <= bound);
       if (TIES && (w0 || w1)) {
         const int2 mi = __ldg(&P.node_min_idx[node]);
-        if (w0) w0 = child_wanted<MODE>(d0, bound, cnt, k, H, heap, mi.x);
-        if (w1) w1 = child_wanted<MODE>(d1, bound, cnt, k, H, heap, mi.y);
+        if (w0) w0 = child_wanted<MODE, S>(d0, bound, cnt, k, H, heap, mi.x);
+        if (w1) w1 = child_wanted<MODE, S>(d1, bound, cnt, k, H, heap, mi.y);
       }
       if (w0 && w1) {
         const bool far0 = __popc(__ballot_sync(FULL_MASK, d1 < d0)) > __popc(__ballot_sync(FULL_MASK, d0 < d1));
@@ -530,7 +611,7 @@ static __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
         int32_t* io = P.idx_out + row * (uint64_t)k;
         float* dd = P.dist_out + row * (uint64_t)k;
         if (P.row_mode && P.qid_out) P.qid_out[row] = row_id;
-        kl_emit<true>(H, cnt, k, heap, P.squared != 0, io, dd);
+        kl_emit<true, S>(H, cnt, k, heap, P.squared != 0, io, dd);
       }
     }
     __syncwarp();

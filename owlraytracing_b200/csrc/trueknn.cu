@@ -1397,11 +1397,11 @@ int tknn_measure_smem_bandwidth(tknn_ctx* c, double* conflict_free_gbs, double* 
   const int iters = 2048;
   for (int mode = 0; mode < 2; ++mode) {
     double best = 0;
-    brute::smem_probe_kernel<<<grid, 256, 0, st>>>(64, mode, sink);  // warm
+    brute::smem_probe_kernel<<<grid, 256, 0, st>>>(64, mode, 264, sink);  // warm
     for (int rep = 0; rep < 5; ++rep) {
       float ms = 0.f;
       TK_CUDA(c, cudaEventRecord(c->ev[0], st));
-      brute::smem_probe_kernel<<<grid, 256, 0, st>>>(iters, mode, sink);
+      brute::smem_probe_kernel<<<grid, 256, 0, st>>>(iters, mode, 264, sink);
       TK_CUDA(c, cudaEventRecord(c->ev[1], st));
       TK_CUDA(c, cudaEventSynchronize(c->ev[1]));
       TK_CUDA(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
