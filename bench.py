@@ -376,7 +376,7 @@ def run_gpu(args):
 
     # ---- build (timed separately) ----
     build_ms, dstats_build = [], None
-    for _ in range(2 if partition else 3):
+    for _ in range(3):
         if partition:
             barrier()
             t.partition_build(xd, lo)
@@ -514,7 +514,7 @@ def run_gpu(args):
                 "timed_region": "search only (estimate + all rounds" + (" + exchange + remote search + merge" if partition else "") +
                                 "), CUDA events on the launching stream, max over ranks; build reported separately",
             },
-            "build_ms": float(np.median(build_ms)),
+            "build_ms": float(np.median(build_ms)), "build_ms_all": [float(v) for v in build_ms],
             "build_phases_ms": ({p: dstats_build[p] for p in ("box_ms", "codes_ms", "splitters_ms", "bucket_ms", "exchange_ms",
                                                               "lbvh_ms", "summaries_ms")} if partition else
                                 {p: bstats[p] for p in ("bounds_ms", "morton_ms", "sort_ms", "leaves_ms", "hierarchy_ms", "refit_ms")}),

@@ -115,6 +115,25 @@ static __global__ void __launch_bounds__(256) cell_hist_kernel(const uint64_t* _
   if (i < n) atomicAdd(&hist[(uint32_t)(codes[i] >> CELL_SHIFT)], 1u);
 }
 
+// sums[b] = number of points in cells [b * SPLIT_BLOCK, (b + 1) * SPLIT_BLOCK): the host finds the block each splitter
+// falls into from these 4096 sums and reads back only those blocks instead of the whole 64 MB histogram
+constexpr int SPLIT_BLOCK = 4096;
+static __global__ void __launch_bounds__(256) cell_block_sums_kernel(const uint32_t* __restrict__ hist, uint64_t* __restrict__ sums) {
+  __shared__ uint64_t s_w[8];
+  const uint32_t* h = hist + (size_t)blockIdx.x * SPLIT_BLOCK;
+  uint64_t v = 0;
+  for (int i = threadIdx.x; i < SPLIT_BLOCK; i += 256) v += h[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t t = 0;
+    for (int w = 0; w < 8; ++w) t += s_w[w];
+    sums[blockIdx.x] = t;
+  }
+}
+
 // keys[i] <- destination rank of point i (in place over its Morton code); counts[r] += points going to rank r
 static __global__ void __launch_bounds__(256) dest_kernel(uint64_t* __restrict__ keys, uint64_t n, Splitters sp, int n_ranks,
                                                           uint32_t* __restrict__ counts) {
@@ -311,9 +330,17 @@ static __global__ void __launch_bounds__(128) merge_reply_kernel(const uint32_t*
   }
 }
 
-static __global__ void __launch_bounds__(256) sqrt_rows_kernel(const int32_t* __restrict__ idx, float* __restrict__ d, uint64_t n) {
+// d2 -> distance in place.  Every rank owns more than k points, so every list is full: there are no -1 / FLT_MAX
+// sentinels to preserve and the index array need not be read.  n4 float4 + a scalar tail.
+static __global__ void __launch_bounds__(256) sqrt_rows_kernel(float* __restrict__ d, uint64_t n, int vec) {
   const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i < n) d[i] = idx[i] >= 0 ? __fsqrt_rn(d[i]) : FLT_MAX;
+  const uint64_t n4 = vec ? n / 4 : 0;
+  if (i < n4) {
+    float4 v = reinterpret_cast<float4*>(d)[i];
+    v.x = __fsqrt_rn(v.x); v.y = __fsqrt_rn(v.y); v.z = __fsqrt_rn(v.z); v.w = __fsqrt_rn(v.w);
+    reinterpret_cast<float4*>(d)[i] = v;
+  }
+  if (i < n - n4 * 4) d[n4 * 4 + i] = __fsqrt_rn(d[n4 * 4 + i]);
 }
 
 // min / max / sum of n_parts blocks of `count` u32 words into the first block (in-process transport)
@@ -735,16 +762,31 @@ static int partition_build(tknn_ctx* c, const float* xyz_local, uint64_t n_local
   // ---- splitters: rank r starts at the first cell whose exclusive prefix reaches r * N / n_ranks ----
   Splitters sp;
   {
-    std::vector<uint32_t> h(N_CELLS);
-    TK_CUDA(c, cudaMemcpyAsync(h.data(), S->hist.p, N_CELLS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    // two levels: 4096 block sums on the device, then only the blocks a splitter falls into are read back
+    constexpr size_t NB = N_CELLS / SPLIT_BLOCK;
+    TK_TRY(ensure(c, S->ver, NB * sizeof(uint64_t)));
+    cell_block_sums_kernel<<<(unsigned)NB, 256, 0, st>>>(S->hist.as<uint32_t>(), S->ver.as<uint64_t>());
+    TK_CUDA(c, cudaGetLastError());
+    std::vector<uint64_t> bs(NB);
+    TK_CUDA(c, cudaMemcpyAsync(bs.data(), S->ver.p, NB * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     TK_CUDA(c, cudaStreamSynchronize(st));
-    uint64_t acc = 0;
-    int r = 1;
-    for (size_t cell = 0; cell < N_CELLS && r < n; ++cell) {
-      while (r < n && acc >= n_global * (uint64_t)r / (uint64_t)n) sp.cell[r++ - 1] = (uint32_t)cell;
-      acc += h[cell];
+    std::vector<uint32_t> blk(SPLIT_BLOCK);
+    uint64_t acc = 0;    // points in the blocks before `b`
+    size_t b = 0;
+    for (int r = 1; r < n; ++r) {
+      const uint64_t target = n_global * (uint64_t)r / (uint64_t)n;
+      while (b < NB && acc + bs[b] < target) { acc += bs[b]; ++b; }  // P(first cell of block b + 1) < target: not in block b
+      // rank r starts at the first cell whose exclusive prefix reaches the target: it lies in block b (or is its first cell)
+      if (b >= NB) { sp.cell[r - 1] = (uint32_t)N_CELLS; continue; }
+      TK_CUDA(c, cudaMemcpyAsync(blk.data(), S->hist.as<uint32_t>() + b * SPLIT_BLOCK, SPLIT_BLOCK * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost, st));
+      TK_CUDA(c, cudaStreamSynchronize(st));
+      uint64_t a2 = acc;
+      size_t cell = 0;
+      while (cell < (size_t)SPLIT_BLOCK && a2 < target) { a2 += blk[cell]; ++cell; }
+      if (a2 < target) { sp.cell[r - 1] = (uint32_t)N_CELLS; continue; }  // cannot happen: the block holds the target
+      sp.cell[r - 1] = (uint32_t)(b * SPLIT_BLOCK + cell);
     }
-    while (r < n) sp.cell[r++ - 1] = (uint32_t)N_CELLS;  // trailing ranks own nothing (degenerate clouds)
     for (int i = n - 1; i < MAX_RANKS; ++i) sp.cell[i] = 0xffffffffu;
   }
   TK_TRY(mark(c, S, 4));
@@ -957,7 +999,8 @@ static int partition_search(tknn_ctx* c, int k, float start_radius, int32_t* gid
   }
   TK_TRY(mark(c, S, 16));
   if (!user_squared) {
-    sqrt_rows_kernel<<<blocks_for(elems, 256), 256, 0, st>>>(d_idx, d_d2, elems);
+    const int vec = (reinterpret_cast<uintptr_t>(d_d2) & 15u) == 0;  // caller-provided arrays may be unaligned
+    sqrt_rows_kernel<<<blocks_for(vec ? elems / 4 + 4 : elems, 256), 256, 0, st>>>(d_d2, elems, vec);
     TK_CUDA(c, cudaGetLastError());
   }
   TK_TRY(mark(c, S, 17));
