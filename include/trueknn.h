@@ -74,6 +74,11 @@ enum {
                                   build found leaves of coincident points), 1 = always, 2 = never           */
   ,TKNN_OPT_WARP_ROUND_MAX = 15 /* rounds with at most this many active queries (the start-radius sample, late rounds of a
                                   few stragglers, small query sets) run one WARP per query (default 49152; 0 = never) */
+  ,TKNN_OPT_CURVE = 16          /* space-filling curve the next build sorts the points by: 0 = Hilbert (default; consecutive
+                                  points are always neighbours in space, so a 32-query group is compact), 1 = Morton */
+  ,TKNN_OPT_SPECULATIVE_MAX = 17 /* searches of at most this many queries run without a host decision between their launches:
+                                  round 2 is launched as the final round before the host knows how many queries round 1 left
+                                  (default 2^20; 0 = always wait for the count) */
   ,TKNN_OPT_SPARSE_DIVISOR = 9 /* rounds >= 2 with fewer than n/divisor active queries run the
                                   thread-per-query kernel (default 8; 0 = never)                  */
 };

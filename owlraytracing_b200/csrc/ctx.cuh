@@ -46,11 +46,14 @@ struct tknn_ctx {
   int keep_scratch = 1;
   int sparse_divisor = 8;
   int warp_round_max = 49152;  // rounds with at most this many active queries run one warp per query (0 = never)
+  int speculative_max = 1 << 20;  // searches of at most this many queries launch round 2 without a host decision (0 = never)
   int approx_filter = 0;
   int tie_pruning = 0;        // 0 = auto (on when the build saw leaves of coincident points), 1 = on, 2 = off
   int morton_bits = 0;        // 0 = auto (ceil(log2 n / 3) + 8, clamped to [10, 21])
   bool has_dup_leaves = false; // the build found a leaf of coincident points => tie-pruning kernel variant
   int built_morton_bits = 21; // what the current BVH was built with (queries are coded the same way)
+  int curve = 1;              // space-filling curve of the next build: 1 = Hilbert (default), 0 = Morton
+  int built_curve = 0;        // Hilbert levels the current BVH's keys were made with (0 = Morton): queries are coded alike
   int output_chunks = 4;  // host-output pipelining: slices whose D2H overlaps the next slice's search (1 = off)
   int file_order_chunks = 4;  // same for tknn_search (file-order rows): slices by original index (1 = off)
   DevBuf chunk_queue;
@@ -80,7 +83,7 @@ inline unsigned blocks_for(uint64_t n, int threads) { return (unsigned)((n + thr
 
 // scalars layout (uint32 words unless noted)
 enum { SC_GROUP_COUNTER = 0, SC_TOTAL = 1, SC_ERROR = 2, SC_QBAD = 3 /* non-finite query coordinate */, SC_BOUNDS = 4 /* 7 words */, SC_SCENE = 12 /* 6 floats */,
-       SC_COUNTERS = 20 /* 8 x u64, 8-byte aligned */, SC_DUPLEAF = 40, SC_QUANTILE = 41, SC_WORDS = 48 };
+       SC_COUNTERS = 20 /* 8 x u64, 8-byte aligned */, SC_DUPLEAF = 40, SC_QUANTILE = 41 /* 2 floats: r, r * r */, SC_WORDS = 48 };
 
 #define TK_CUDA(c, expr)                                                                            \
   do {                                                                                              \

@@ -176,30 +176,53 @@ static __global__ void __launch_bounds__(256) dense_xyz_kernel(const float* __re
 
 // Tight box of this rank's points inside every top-level cell of the GLOBAL grid (same quantiser as morton_kernel).
 // boxes: [512][6] order-preserving uints (min xyz, max xyz), initialised to (~0, ~0, ~0, 0, 0, 0).
+// The points are Morton-sorted on (nearly) the same grid, so a cell is one long run of consecutive points: a warp
+// walks CELL_RUN consecutive points (coalesced, 32 per step), every lane accumulating a private box that it flushes
+// with atomics only when its cell changes; at the end a warp whose lanes all sit in one cell reduces with shuffles and
+// issues ONE set of six atomics.  (The first version issued six atomics per warp of 32 points onto the same few
+// addresses: 53 ms for 250 M points; profiles/r2_bench_cfg5_2B_n8.json.)
+constexpr int CELL_RUN = 2048;
+__device__ __forceinline__ void flush_cell_box(uint32_t* __restrict__ boxes, uint32_t cell, const float lo[3], const float hi[3]) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    atomicMin(&boxes[cell * 6 + a], float_to_ordered(lo[a]));
+    atomicMax(&boxes[cell * 6 + 3 + a], float_to_ordered(hi[a]));
+  }
+}
+
 static __global__ void __launch_bounds__(256) cell_boxes_kernel(const float4* __restrict__ pts, uint64_t n,
                                                                 const float* __restrict__ box6, uint32_t* __restrict__ boxes) {
-  const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-  const bool valid = i < n;
-  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-  uint32_t cell = 0xffffffffu;
-  if (valid) {
-    p = __ldg(&pts[i]);
-    const float lx = box6[0], ly = box6[1], lz = box6[2];
-    const float ext = fmaxf(fmaxf(box6[3] - lx, box6[4] - ly), fmaxf(box6[5] - lz, FLT_MIN));
-    const float scale = 2097152.0f / ext;
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp_id = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+  const uint64_t begin = warp_id * CELL_RUN;
+  if (begin >= n) return;
+  const uint64_t end = begin + CELL_RUN < n ? begin + CELL_RUN : n;
+  const float lx = box6[0], ly = box6[1], lz = box6[2];
+  const float ext = fmaxf(fmaxf(box6[3] - lx, box6[4] - ly), fmaxf(box6[5] - lz, FLT_MIN));
+  const float scale = 2097152.0f / ext;
+  uint32_t cur = 0xffffffffu;  // no cell yet
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (uint64_t i = begin + lane; i < end; i += 32) {
+    const float4 p = __ldg(&pts[i]);
     const uint32_t cx = (uint32_t)fminf(fmaxf((p.x - lx) * scale, 0.0f), 2097151.0f) >> (21 - SUMMARY_AXIS_BITS);
     const uint32_t cy = (uint32_t)fminf(fmaxf((p.y - ly) * scale, 0.0f), 2097151.0f) >> (21 - SUMMARY_AXIS_BITS);
     const uint32_t cz = (uint32_t)fminf(fmaxf((p.z - lz) * scale, 0.0f), 2097151.0f) >> (21 - SUMMARY_AXIS_BITS);
-    cell = 0;
+    uint32_t cell = 0;
 #pragma unroll
     for (int b = 0; b < SUMMARY_AXIS_BITS; ++b)
       cell |= ((cx >> b) & 1u) << (3 * b + 2) | ((cy >> b) & 1u) << (3 * b + 1) | ((cz >> b) & 1u) << (3 * b);
+    if (cell != cur) {
+      if (cur != 0xffffffffu) flush_cell_box(boxes, cur, lo, hi);
+      cur = cell;
+      lo[0] = hi[0] = p.x; lo[1] = hi[1] = p.y; lo[2] = hi[2] = p.z;
+    } else {
+      lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+      hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+    }
   }
-  // the points are Morton-sorted on (nearly) the same grid: a warp usually sits in one cell -> one set of atomics
-  const uint32_t c0 = __shfl_sync(FULL_MASK, cell, 0);
-  if (__all_sync(FULL_MASK, cell == c0)) {
-    if (c0 == 0xffffffffu) return;
-    float lo[3] = {p.x, p.y, p.z}, hi[3] = {p.x, p.y, p.z};
+  // the run is over: one set of atomics per warp when every lane ended in the same cell (lanes without a point agree)
+  const uint32_t c0 = __shfl_sync(FULL_MASK, cur, 0);
+  if (__all_sync(FULL_MASK, cur == c0 || cur == 0xffffffffu) && c0 != 0xffffffffu) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
@@ -207,18 +230,9 @@ static __global__ void __launch_bounds__(256) cell_boxes_kernel(const float4* __
         lo[a] = fminf(lo[a], __shfl_xor_sync(FULL_MASK, lo[a], o));
         hi[a] = fmaxf(hi[a], __shfl_xor_sync(FULL_MASK, hi[a], o));
       }
-    if ((threadIdx.x & 31) < 3) {
-      const int a = threadIdx.x & 31;
-      atomicMin(&boxes[c0 * 6 + a], float_to_ordered(lo[a]));
-      atomicMax(&boxes[c0 * 6 + 3 + a], float_to_ordered(hi[a]));
-    }
-  } else if (valid) {
-    atomicMin(&boxes[cell * 6 + 0], float_to_ordered(p.x));
-    atomicMin(&boxes[cell * 6 + 1], float_to_ordered(p.y));
-    atomicMin(&boxes[cell * 6 + 2], float_to_ordered(p.z));
-    atomicMax(&boxes[cell * 6 + 3], float_to_ordered(p.x));
-    atomicMax(&boxes[cell * 6 + 4], float_to_ordered(p.y));
-    atomicMax(&boxes[cell * 6 + 5], float_to_ordered(p.z));
+    if (lane == 0) flush_cell_box(boxes, c0, lo, hi);
+  } else if (cur != 0xffffffffu) {
+    flush_cell_box(boxes, cur, lo, hi);
   }
 }
 
@@ -752,7 +766,7 @@ static int partition_build(tknn_ctx* c, const float* xyz_local, uint64_t n_local
   uint32_t* vals = c->b_vals_a.as<uint32_t>();
   TK_CUDA(c, cudaMemsetAsync(S->hist.p, 0, N_CELLS * sizeof(uint32_t), st));
   if (n_local) {
-    lbvh::morton_kernel<<<blocks_for(n_local, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, n_local, dim, stride, ob, 21, keys, vals);
+    lbvh::morton_kernel<<<blocks_for(n_local, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, n_local, dim, stride, ob, 21, 0, keys, vals);
     cell_hist_kernel<<<blocks_for(n_local, 256), 256, 0, st>>>(keys, n_local, S->hist.as<uint32_t>());
     TK_CUDA(c, cudaGetLastError());
   }
@@ -848,7 +862,8 @@ static int partition_build(tknn_ctx* c, const float* xyz_local, uint64_t n_local
     for (int b = 0; b < SUMMARY_BOXES; ++b)
       for (int a = 0; a < 6; ++a) init[(size_t)b * 6 + a] = a < 3 ? 0xffffffffu : 0u;
     TK_CUDA(c, cudaMemcpyAsync(S->boxes_ord.p, init.data(), init.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    cell_boxes_kernel<<<blocks_for(n_owned, 256), 256, 0, st>>>(c->pts.as<float4>(), n_owned, gbox_f, S->boxes_ord.as<uint32_t>());
+    cell_boxes_kernel<<<blocks_for((n_owned + CELL_RUN - 1) / CELL_RUN * 32, 256), 256, 0, st>>>(c->pts.as<float4>(), n_owned, gbox_f,
+                                                                                          S->boxes_ord.as<uint32_t>());
     boxes_to_float_kernel<<<blocks_for(SUMMARY_BOXES, 128), 128, 0, st>>>(S->boxes_ord.as<uint32_t>(), SUMMARY_BOXES,
                                                                        S->summ_mine.as<float>());
     TK_CUDA(c, cudaGetLastError());

@@ -81,8 +81,36 @@ __device__ __forceinline__ uint64_t spread21(uint32_t v) {
   return x;
 }
 
+// Hilbert index of a cell of the 2^bits cubic grid in "transposed" form (Skilling 2004, AxesToTranspose): afterwards the
+// three words hold the index's bits interleaved exactly like a Morton code holds the coordinates' bits, so the same
+// spread21 interleave yields the key.  A Hilbert key has the Morton key's prefix property — the first 3 m bits name the
+// same octree cell at level m, only the order of the eight children differs — so the leaf cut and the Karras hierarchy
+// see the same cells and build the same tree up to child order.  What changes is the ORDER of the points: consecutive
+// points on the Hilbert curve are always neighbours in space, while the Z-curve jumps at every octant seam.  The
+// traversal's work unit is 32 consecutive sorted points whose balls are searched TOGETHER: on 2 M uniform points the
+// bounding box of such a group, inflated by the k-th-neighbour radius, holds 245 points on average along the Hilbert
+// curve and 427 along the Z-curve (p90: 306 vs 642).
+__device__ __forceinline__ void hilbert_transpose(uint32_t& x0, uint32_t& x1, uint32_t& x2, int bits) {
+  for (uint32_t q = 1u << (bits - 1); q > 1u; q >>= 1) {
+    const uint32_t p = q - 1u;
+    if (x0 & q) x0 ^= p;  // axis 0: invert (the exchange with itself is the identity)
+    if (x1 & q) x0 ^= p; else { const uint32_t t = (x0 ^ x1) & p; x0 ^= t; x1 ^= t; }
+    if (x2 & q) x0 ^= p; else { const uint32_t t = (x0 ^ x2) & p; x0 ^= t; x2 ^= t; }
+  }
+  x1 ^= x0;  // Gray encode
+  x2 ^= x1;
+  uint32_t t = x2 >> 1;  // t bit j = xor of the bits of x2 above j
+  t ^= t >> 1; t ^= t >> 2; t ^= t >> 4; t ^= t >> 8; t ^= t >> 16;
+  x0 ^= t; x1 ^= t; x2 ^= t;
+}
+
+// curve: 0 = Morton (Z-order); h > 0 = Hilbert order on the top h bits per axis, Morton order below.  The curve only
+// has to keep consecutive points together down to the level where a cell holds about one point (log2(n) / 3 bits per
+// axis); the builder asks for two levels more.  Below that the digits stay plain Morton digits — each still names one
+// octant of its cell, so the key keeps its prefix property — and the transform loop is 40 % shorter (10 of 16 levels
+// at 10 M points: 0.22 -> 0.15 ms).
 static __global__ void __launch_bounds__(THREADS) morton_kernel(const float* __restrict__ xyz, uint64_t n, int dim, int stride,
-                                                         const uint32_t* __restrict__ bounds, int bits,
+                                                         const uint32_t* __restrict__ bounds, int bits, int curve,
                                                          uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   const uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
   if (i >= n) return;
@@ -93,11 +121,20 @@ static __global__ void __launch_bounds__(THREADS) morton_kernel(const float* __r
   const float scale = 2097152.0f / ext;  // 2^21 cells along the longest axis
   const float* p = xyz + i * (uint64_t)stride;
   const float x = p[0], y = p[1], z = dim > 2 ? p[2] : 0.0f;
-  const uint32_t cx = (uint32_t)fminf(fmaxf((x - lx) * scale, 0.0f), 2097151.0f);
-  const uint32_t cy = (uint32_t)fminf(fmaxf((y - ly) * scale, 0.0f), 2097151.0f);
-  const uint32_t cz = (uint32_t)fminf(fmaxf((z - lz) * scale, 0.0f), 2097151.0f);
   const int drop = 21 - bits;  // keep the top `bits` bits of each 21-bit coordinate
-  keys[i] = (spread21(cx >> drop) << 2) | (spread21(cy >> drop) << 1) | spread21(cz >> drop);
+  uint32_t cx = (uint32_t)fminf(fmaxf((x - lx) * scale, 0.0f), 2097151.0f) >> drop;
+  uint32_t cy = (uint32_t)fminf(fmaxf((y - ly) * scale, 0.0f), 2097151.0f) >> drop;
+  uint32_t cz = (uint32_t)fminf(fmaxf((z - lz) * scale, 0.0f), 2097151.0f) >> drop;
+  if (curve > 0) {
+    const int h = curve < bits ? curve : bits, low = bits - h;
+    uint32_t hx = cx >> low, hy = cy >> low, hz = cz >> low;
+    hilbert_transpose(hx, hy, hz, h);
+    const uint32_t lm = (1u << low) - 1u;
+    cx = (hx << low) | (cx & lm);
+    cy = (hy << low) | (cy & lm);
+    cz = (hz << low) | (cz & lm);
+  }
+  keys[i] = (spread21(cx) << 2) | (spread21(cy) << 1) | spread21(cz);
   vals[i] = (uint32_t)i;
 }
 

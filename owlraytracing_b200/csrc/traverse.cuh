@@ -53,6 +53,10 @@ struct Params {
   uint32_t* count_out;       // MODE_RANGE_COUNT
   uint32_t* unresolved;      // one ballot word per group
   uint32_t* group_counter;   // persistent-grid work counter
+  const float* r2_dev;           // optional: the squared radius of this round, read from device memory (the start-radius
+                                 // estimate stays on the device: no host round trip before round 1); overrides r2
+  const uint32_t* n_active_dev;  // optional: min(*n_active_dev, n_active) queries are active (a round launched before the
+                                 // host knows how many queries the previous round left unresolved)
   unsigned long long* counters;  // [0] node visits x active lanes, [1] point tests x active lanes, [2] inserts,
                                  // [3] warp node loads, [4] warp leaf loads, [5] warp point loads,
                                  // [6] pre-filter violations (must stay 0)
@@ -394,15 +398,18 @@ static __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
   if (HEAP && MODE == MODE_KNN) {  // zero padding behind the heap (never written again)
     for (int j = 0; j < heap_pads(k); ++j) H[(k + 1 + j) * 32] = 0;
   }
+  const float round_r2 = P.r2_dev ? __ldg(P.r2_dev) : P.r2;
+  const uint64_t n_active = P.n_active_dev ? min((uint64_t)__ldg(P.n_active_dev), P.n_active) : P.n_active;
+  const uint32_t n_groups = (uint32_t)((n_active + 31) / 32);
 
   for (;;) {
     uint32_t group = 0;
     if (lane == 0) group = atomicAdd(P.group_counter, 1u);
     group = __shfl_sync(FULL_MASK, group, 0);
-    if (group >= P.n_groups) break;
+    if (group >= n_groups) break;
 
     const uint64_t gi = (uint64_t)group * 32 + lane;
-    const bool valid = gi < P.n_active;
+    const bool valid = gi < n_active;
     uint64_t qpos = 0;
     if (valid) qpos = P.queue ? (uint64_t)P.queue[gi] : P.q_begin + gi;
     float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -410,7 +417,7 @@ static __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
     const int row_id = __float_as_int(q.w);
     int self = -1;
     if (valid) self = P.self_ids ? P.self_ids[qpos] : (P.self_is_row ? row_id : -1);
-    float r2 = P.r2;
+    float r2 = round_r2;
     if (valid && P.query_r2) r2 = fminf(r2, P.query_r2[qpos]);
     float bound = valid ? r2 : -1.0f;  // d2 >= 0 > -1: an idle lane never wants anything
     int cnt = 0;
@@ -654,7 +661,8 @@ static __global__ void __launch_bounds__(SPARSE_THREADS) traverse_sparse_kernel(
   unsigned long long c_nodes = 0, c_tests = 0, c_ins = 0;
 
   const uint64_t gi = (uint64_t)blockIdx.x * SPARSE_THREADS + threadIdx.x;
-  const bool valid = gi < P.n_active;
+  const uint64_t n_active = P.n_active_dev ? min((uint64_t)__ldg(P.n_active_dev), P.n_active) : P.n_active;
+  const bool valid = gi < n_active;
   uint64_t qpos = 0;
   if (valid) qpos = P.queue ? (uint64_t)P.queue[gi] : P.q_begin + gi;
   float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -662,7 +670,7 @@ static __global__ void __launch_bounds__(SPARSE_THREADS) traverse_sparse_kernel(
   const int row_id = __float_as_int(q.w);
   int self = -1;
   if (valid) self = P.self_ids ? P.self_ids[qpos] : (P.self_is_row ? row_id : -1);
-  float r2 = P.r2;
+  float r2 = P.r2_dev ? __ldg(P.r2_dev) : P.r2;
   if (valid && P.query_r2) r2 = fminf(r2, P.query_r2[qpos]);
   float bound = r2;
   int cnt = 0;
@@ -737,7 +745,7 @@ static __global__ void __launch_bounds__(SPARSE_THREADS) traverse_sparse_kernel(
 
   const bool resolved = valid && cnt == k;
   const unsigned un = __ballot_sync(FULL_MASK, valid && !resolved);
-  if (lane == 0 && P.unresolved && (gi >> 5) < P.n_groups) P.unresolved[gi >> 5] = un;
+  if (lane == 0 && P.unresolved && (gi >> 5) < P.n_groups) P.unresolved[gi >> 5] = un;  // P.n_groups: the launch's capacity
   if (valid && (resolved || P.final_round)) {
     const uint64_t row = P.row_mode == 0 ? (uint64_t)(uint32_t)row_id : (P.row_mode == 1 ? qpos - P.q_begin : gi);
     int32_t* io = P.idx_out + row * (uint64_t)k;
@@ -803,12 +811,13 @@ static __global__ void __launch_bounds__(WQ_WARPS * 32) traverse_warp_kernel(con
   uint64_t* L = reinterpret_cast<uint64_t*>(smem) + (size_t)warp * k;
   int* stack = reinterpret_cast<int*>(smem + (size_t)WQ_WARPS * k * sizeof(uint64_t)) + warp * STACK_DEPTH;
   const uint64_t gi = (uint64_t)blockIdx.x * WQ_WARPS + warp;
-  if (gi >= P.n_active) return;  // the whole warp leaves; the kernel has no block-wide barrier
+  const uint64_t n_active = P.n_active_dev ? min((uint64_t)__ldg(P.n_active_dev), P.n_active) : P.n_active;
+  if (gi >= n_active) return;  // the whole warp leaves; the kernel has no block-wide barrier
   const uint64_t qpos = P.queue ? (uint64_t)P.queue[gi] : P.q_begin + gi;
   const float4 q = __ldg(&P.queries[qpos]);
   const int row_id = __float_as_int(q.w);
   const int self = P.self_ids ? P.self_ids[qpos] : (P.self_is_row ? row_id : -1);
-  float bound = P.r2;
+  float bound = P.r2_dev ? __ldg(P.r2_dev) : P.r2;
   if (P.query_r2) bound = fminf(bound, P.query_r2[qpos]);
   int cnt = 0;
   uint64_t worst = ~0ull;  // L[k - 1] once the list is full
@@ -913,6 +922,59 @@ static __global__ void __launch_bounds__(WQ_WARPS * 32) traverse_warp_kernel(con
     atomicAdd(&P.counters[2], c_ins);
     atomicAdd(&P.counters[3], c_nodes);
     atomicAdd(&P.counters[5], c_tests);
+  }
+}
+
+// Start-radius estimator, device side.  The sample = `sg` runs of 32 consecutive sorted positions spread evenly over
+// the `groups` groups of the query range (only the last group of the range can be short, and it is the last run).
+static __global__ void __launch_bounds__(256) sample_queue_kernel(uint64_t groups, uint32_t sg, uint64_t q_begin, uint64_t nq,
+                                                                  uint32_t* __restrict__ queue) {
+  const uint32_t t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= sg * 32u) return;
+  const uint64_t g = groups * (uint64_t)(t >> 5) / sg;
+  const uint64_t pos = g * 32 + (t & 31u);
+  if (pos < nq) queue[t] = (uint32_t)(q_begin + pos);
+}
+
+// out[0] = the `pos`-th smallest (0-based) of the m sampled k-th-neighbour distances dist[i * k + k - 1], out[1] = its
+// square (the round's r2, the same fp32 product the host forms).  Radix select over the bit patterns (non-negative
+// floats order like unsigned ints): four 8-bit passes of one block.  A degenerate sample (the quantile is 0: duplicate
+// clusters) falls back to the largest finite positive value, or +inf (one unbounded round) when there is none.
+static __global__ void __launch_bounds__(1024) radius_quantile_kernel(const float* __restrict__ dist, uint32_t m, int k, uint32_t pos,
+                                                                      float* __restrict__ out) {
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_prefix, s_want, s_maxpos;
+  uint32_t prefix = 0, mask = 0, want = pos;
+  if (threadIdx.x == 0) s_maxpos = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < m; i += 1024) {
+      const uint32_t u = __float_as_uint(dist[(uint64_t)i * k + (k - 1)]);
+      if ((u & mask) == prefix) atomicAdd(&s_hist[(u >> shift) & 255u], 1u);
+      if (shift == 24 && u > 0u && u < 0x7f800000u) atomicMax(&s_maxpos, u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t acc = 0;
+      int b = 0;
+      for (; b < 255; ++b) {
+        if (acc + s_hist[b] > want) break;
+        acc += s_hist[b];
+      }
+      s_prefix = prefix | ((uint32_t)b << shift);
+      s_want = want - acc;
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    want = s_want;
+    mask |= 0xffu << shift;
+  }
+  if (threadIdx.x == 0) {
+    float r = __uint_as_float(prefix);
+    if (!(r > 0.0f) || !isfinite(r)) r = s_maxpos ? __uint_as_float(s_maxpos) : INFINITY;
+    out[0] = r;
+    out[1] = __fmul_rn(r, r);
   }
 }
 

@@ -97,7 +97,10 @@ struct Job {
   int self_is_row = 0;
   int row_mode = 0;
   int k = 0;
-  float start_radius = 0.f;  // > 0 or +inf
+  float start_radius = 0.f;  // > 0 or +inf; ignored while r_dev is set
+  const float* r_dev = nullptr;  // {r, r * r} on the device (the estimator's output): round 1 reads r2 from there and the
+                                 // host learns r with the first read-back it needs anyway
+  float* r_host = nullptr;       // receives the radius round 1 ran with
   int squared = 0;
   int32_t* idx_out = nullptr;
   float* dist_out = nullptr;
@@ -197,6 +200,14 @@ int launch_traverse_warp(tknn_ctx* c, const trav::Params& P) {
   return TKNN_OK;
 }
 
+// One round = one traversal launch over the active queries; unresolved ones are compacted (order preserved) into the
+// next round's queue and the radius doubles (hostCode.cpp:285-340 without the refits).
+//
+// Small searches are latency bound (cfg1: 100 K queries, 0.15 ms of kernels), so the common case makes NO host decision
+// between its launches: round 1 reads its radius from the device (the estimator's output), the compaction runs
+// unconditionally, and round 2 is launched SPECULATIVELY as the final, unbounded round of one warp per query over at most
+// `cap` queue entries with the true count read on the device.  The host then reads {count, radius} once.  Only when more
+// than `cap` queries were left (a far too small user radius) does the doubling loop continue for the rest.
 int run_rounds(tknn_ctx* c, const Job& job, int* launches_io) {
   uint32_t* sc = c->scalars.as<uint32_t>();
   const uint64_t n0 = job.n_queries;
@@ -207,14 +218,17 @@ int run_rounds(tknn_ctx* c, const Job& job, int* launches_io) {
   const float diag = std::sqrt((c->scene_box[3] - c->scene_box[0]) * (c->scene_box[3] - c->scene_box[0]) +
                                (c->scene_box[4] - c->scene_box[1]) * (c->scene_box[4] - c->scene_box[1]) +
                                (c->scene_box[5] - c->scene_box[2]) * (c->scene_box[5] - c->scene_box[2]));
-  float radius = job.start_radius;
+  float radius = job.r_dev ? 0.0f : job.start_radius;  // with r_dev: known after the first read-back
+  bool radius_known = job.r_dev == nullptr;
   uint64_t active = n0;
   const uint32_t* queue = job.first_queue;
+  DevBuf* qbuf = nullptr;  // which of queue_a / queue_b holds `queue` (nullptr: the caller's first queue, or none)
   int round = 0;
   int launches = 0;
-  while (active > 0) {
-    const bool last = std::isinf(radius) || radius > 2.0f * diag || round >= TKNN_MAX_ROUNDS - 1;
-    trav::Params P;
+  const uint64_t spec_cap = std::min<uint64_t>(n0, (uint64_t)std::max(0, c->warp_round_max));
+  const bool speculate = c->speculative_max > 0 && n0 <= (uint64_t)c->speculative_max && spec_cap > 0;
+
+  auto fill = [&](trav::Params& P, bool last) {
     std::memset(&P, 0, sizeof(P));
     P.nodes = c->nodes.as<Node>();
     P.node_min_idx = c->node_min_idx.as<int2>();
@@ -239,18 +253,40 @@ int run_rounds(tknn_ctx* c, const Job& job, int* launches_io) {
     P.unresolved = last ? nullptr : c->unresolved.as<uint32_t>();
     P.group_counter = sc + SC_GROUP_COUNTER;
     P.counters = c->counters ? reinterpret_cast<unsigned long long*>(sc + SC_COUNTERS) : nullptr;
+  };
+  auto round_events = [&](int r) -> int {
+    while ((int)c->round_ev.size() < 4 * (r + 1)) {
+      cudaEvent_t a;
+      TK_CUDA(c, cudaEventCreate(&a));
+      c->round_ev.push_back(a);
+    }
+    return TKNN_OK;
+  };
+  // {unresolved count, radius} in one read-back: the one host decision of a round (hostCode.cpp:310-330)
+  auto read_back = [&](uint32_t* count) -> int {
+    struct { uint32_t total; float r; } h = {0, 0.f};
+    TK_CUDA(c, cudaMemcpyAsync(&h.total, sc + SC_TOTAL, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (!radius_known) TK_CUDA(c, cudaMemcpyAsync(&h.r, job.r_dev, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    TK_CUDA(c, cudaStreamSynchronize(c->stream));
+    *count = h.total;
+    if (!radius_known) { radius = h.r; radius_known = true; if (job.r_host) *job.r_host = h.r; }
+    return TKNN_OK;
+  };
 
-    if (job.record_stats && round < TKNN_MAX_ROUNDS) {
-      while ((int)c->round_ev.size() < 4 * (round + 1)) {
-        cudaEvent_t a;
-        TK_CUDA(c, cudaEventCreate(&a));
-        c->round_ev.push_back(a);
-      }
+  while (active > 0) {
+    // a radius the host does not know yet (r_dev) is never treated as the last round: the estimator's fallback for a
+    // degenerate sample is +inf, and a round at r2 = +inf resolves every query that has k neighbours at all
+    const bool last = radius_known && (std::isinf(radius) || radius > 2.0f * diag || round >= TKNN_MAX_ROUNDS - 1);
+    trav::Params P;
+    fill(P, last);
+    if (!radius_known) P.r2_dev = job.r_dev + 1;
+    const bool timed = job.record_stats && round < TKNN_MAX_ROUNDS;
+    if (timed) {
+      TK_TRY(round_events(round));
       TK_CUDA(c, cudaEventRecord(c->round_ev[4 * round], c->stream));
       c->stats.round_queries[round] = active;
     }
     TK_CUDA(c, cudaMemsetAsync(sc + SC_GROUP_COUNTER, 0, sizeof(uint32_t), c->stream));
-    const bool timed = job.record_stats && round < TKNN_MAX_ROUNDS;
     if (timed) TK_CUDA(c, cudaEventRecord(c->round_ev[4 * round + 2], c->stream));
     // sparse remainder (< 1/sparse_divisor of the round-1 queries, taken from a queue): one thread per query
     const bool sparse = trav::sparse_smem(job.k) <= 200 * 1024 &&
@@ -267,15 +303,53 @@ int run_rounds(tknn_ctx* c, const Job& job, int* launches_io) {
     if (!last) {
       // order-preserving compaction of the unresolved queries (ballot words + prefix sums)
       TK_TRY(popc_scan(c, c->unresolved.as<uint32_t>(), P.n_groups, c->offsets.as<uint32_t>(), &launches));
-      TK_CUDA(c, cudaMemcpyAsync(&next_active, sc + SC_TOTAL, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-      TK_CUDA(c, cudaStreamSynchronize(c->stream));  // the one host decision per round (hostCode.cpp:310-330)
+      DevBuf& qout = (qbuf == &c->queue_a) ? c->queue_b : c->queue_a;
+      if (speculate && round == 0) {
+        // ---- no host decision: compact everything, run the final round over <= spec_cap entries, then look ----
+        TK_TRY(ensure(c, qout, sizeof(uint32_t) * (size_t)n0));
+        trav::compact_queue_kernel<<<blocks_for((uint64_t)P.n_groups * 32, 256), 256, 0, c->stream>>>(
+            c->unresolved.as<uint32_t>(), c->offsets.as<uint32_t>(), P.n_groups, queue, job.q_begin, qout.as<uint32_t>());
+        ++launches;
+        if (timed) TK_CUDA(c, cudaEventRecord(c->round_ev[4 * round + 1], c->stream));
+        queue = qout.as<uint32_t>();
+        qbuf = &qout;
+        active = spec_cap;
+        trav::Params F;
+        fill(F, true);
+        F.n_active_dev = sc + SC_TOTAL;
+        const bool timed2 = job.record_stats && round + 1 < TKNN_MAX_ROUNDS;
+        if (timed2) {
+          TK_TRY(round_events(round + 1));
+          TK_CUDA(c, cudaEventRecord(c->round_ev[4 * (round + 1)], c->stream));
+          TK_CUDA(c, cudaEventRecord(c->round_ev[4 * (round + 1) + 2], c->stream));
+        }
+        TK_TRY(launch_traverse_warp(c, F));
+        ++launches;
+        if (timed2) {
+          TK_CUDA(c, cudaEventRecord(c->round_ev[4 * (round + 1) + 3], c->stream));
+          TK_CUDA(c, cudaEventRecord(c->round_ev[4 * (round + 1) + 1], c->stream));
+        }
+        TK_TRY(read_back(&next_active));
+        ++round;  // round 1 is done
+        if (next_active > 0) {
+          if (timed2) c->stats.round_queries[round] = std::min<uint64_t>(next_active, spec_cap);
+          ++round;  // ... and so is the speculative final round
+        }
+        radius *= 2.0f;
+        if (next_active <= spec_cap) { active = 0; break; }
+        // more queries were left than the speculative round covered: the doubling loop takes the rest of the queue
+        queue = queue + spec_cap;
+        active = next_active - spec_cap;
+        continue;
+      }
+      TK_TRY(read_back(&next_active));
       if (next_active > 0) {
-        DevBuf& qout = (queue == c->queue_a.as<uint32_t>()) ? c->queue_b : c->queue_a;
         TK_TRY(ensure(c, qout, sizeof(uint32_t) * (size_t)next_active));
         trav::compact_queue_kernel<<<blocks_for((uint64_t)P.n_groups * 32, 256), 256, 0, c->stream>>>(
             c->unresolved.as<uint32_t>(), c->offsets.as<uint32_t>(), P.n_groups, queue, job.q_begin, qout.as<uint32_t>());
         ++launches;
         queue = qout.as<uint32_t>();
+        qbuf = &qout;
       }
     }
     if (timed) TK_CUDA(c, cudaEventRecord(c->round_ev[4 * round + 1], c->stream));
@@ -283,36 +357,34 @@ int run_rounds(tknn_ctx* c, const Job& job, int* launches_io) {
     active = next_active;
     if (!last) radius *= 2.0f;
   }
+  if (!radius_known && job.r_host) {  // a single final round ran on a device radius: fetch it for the statistics
+    uint32_t dummy = 0;
+    TK_TRY(read_back(&dummy));
+  }
   if (job.record_stats) {
     c->stats.rounds = round;
-    c->stats.final_radius = round > 0 ? radius : job.start_radius;
+    c->stats.final_radius = radius;
   }
   if (launches_io) *launches_io += launches;
   return TKNN_OK;
 }
 
-// Sampled k-th-neighbour distance -> start radius (role of Util/random_sample.py:5-32).
-int estimate_radius(tknn_ctx* c, const float4* queries, uint64_t q_begin, uint64_t nq, const int32_t* self_ids,
-                    int self_is_row, int k, float* out, int* launches) {
-  // sample_groups runs of 32 consecutive sorted positions: the 32 threads of a warp of the thread-per-query
-  // kernel then walk nearly the same nodes and leaves (shared cache lines, similar trip counts)
+// Sampled k-th-neighbour distance -> start radius (role of Util/random_sample.py:5-32), entirely on the device: the
+// sample queue is generated by a kernel, the sampled queries run one unbounded final round (one warp per query), and a
+// one-block radix select leaves {r, r * r} at sc[SC_QUANTILE].  Nothing is copied and nothing waits: round 1 reads r2
+// from there (Job::r_dev).
+int estimate_radius_device(tknn_ctx* c, const float4* queries, uint64_t q_begin, uint64_t nq, const int32_t* self_ids,
+                           int self_is_row, int k, int* launches) {
+  // sample_groups runs of 32 consecutive sorted positions: neighbouring queries walk nearly the same nodes and leaves
   const uint64_t groups = (nq + 31) / 32;
   const uint64_t sg = std::min<uint64_t>((uint64_t)std::max(1, c->sample_groups), groups);
-  std::vector<uint32_t> q;
-  q.reserve(sg * 32);
-  for (uint64_t s = 0; s < sg; ++s) {
-    const uint64_t g = (groups * s) / sg;
-    for (int l = 0; l < 32; ++l) {
-      const uint64_t pos = g * 32 + l;
-      if (pos < nq) q.push_back((uint32_t)(q_begin + pos));
-    }
-  }
-  const size_t m = q.size();
+  uint64_t m = sg * 32;  // only the last group of the range can be short, and only the last run can be that group
+  if (groups * (sg - 1) / sg == groups - 1 && (nq & 31)) m -= 32 - (nq & 31);
   TK_TRY(ensure(c, c->sample, m * sizeof(uint32_t) + m * (size_t)k * (sizeof(int32_t) + sizeof(float))));
   uint32_t* dq = c->sample.as<uint32_t>();
   int32_t* di = reinterpret_cast<int32_t*>(dq + m);
   float* dd = reinterpret_cast<float*>(di + m * (size_t)k);
-  TK_CUDA(c, cudaMemcpyAsync(dq, q.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  trav::sample_queue_kernel<<<blocks_for(sg * 32, 256), 256, 0, c->stream>>>(groups, (uint32_t)sg, q_begin, nq, dq);
   Job job;
   job.queries = queries;
   job.self_ids = self_ids;
@@ -333,21 +405,11 @@ int estimate_radius(tknn_ctx* c, const float4* queries, uint64_t q_begin, uint64
   int rc = run_rounds(c, job, launches);
   c->counters = saved;
   TK_TRY(rc);
-  std::vector<float> h(m * (size_t)k);
-  TK_CUDA(c, cudaMemcpyAsync(h.data(), dd, h.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  TK_CUDA(c, cudaStreamSynchronize(c->stream));
-  std::vector<float> kth(m);
-  for (size_t i = 0; i < m; ++i) kth[i] = h[i * k + (k - 1)];
-  size_t pos = (size_t)((double)(m - 1) * std::min(1000, std::max(0, c->radius_quantile)) / 1000.0);
-  std::nth_element(kth.begin(), kth.begin() + pos, kth.end());
-  float r = kth[pos];
-  if (!(r > 0.0f) || !std::isfinite(r)) {
-    // degenerate sample (duplicates): fall back to the largest finite positive value, else unbounded
-    r = 0.0f;
-    for (float v : kth) if (std::isfinite(v) && v > r) r = v;
-    if (!(r > 0.0f)) r = INFINITY;
-  }
-  *out = r;
+  const uint32_t pos = (uint32_t)((double)(m - 1) * std::min(1000, std::max(0, c->radius_quantile)) / 1000.0);
+  trav::radius_quantile_kernel<<<1, 1024, 0, c->stream>>>(dd, (uint32_t)m, k, pos,
+                                                          reinterpret_cast<float*>(c->scalars.as<uint32_t>() + SC_QUANTILE));
+  TK_CUDA(c, cudaGetLastError());
+  if (launches) *launches += 2;
   return TKNN_OK;
 }
 
@@ -355,6 +417,13 @@ int auto_morton_bits(uint64_t n) {
   int lg = 0;
   while (((uint64_t)1 << lg) < n) ++lg;
   return std::min(21, std::max(10, (lg + 2) / 3 + 8));
+}
+
+// Hilbert levels of the key kernel (lbvh.cuh: morton_kernel): two levels below the one where a cell holds one point
+int hilbert_levels(uint64_t n, int bits) {
+  int lg = 0;
+  while (((uint64_t)1 << lg) < n) ++lg;
+  return std::max(2, std::min(bits, (lg + 2) / 3 + 2));
 }
 
 int check_ctx(tknn_ctx* c) { return c ? TKNN_OK : TKNN_EINVAL; }
@@ -446,13 +515,16 @@ int tknn::host::search_range(tknn_ctx* c, int k, float start_radius, uint64_t q_
   TK_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
   int launches = 0;
   float r0 = start_radius;
-  if (nq > 0 && !(r0 > 0.0f)) {
-    TK_TRY(estimate_radius(c, c->pts.as<float4>(), q_begin, nq, nullptr, 1, k, &r0, &launches));
-  }
+  const bool estimated = nq > 0 && !(r0 > 0.0f);
+  if (estimated) TK_TRY(estimate_radius_device(c, c->pts.as<float4>(), q_begin, nq, nullptr, 1, k, &launches));
   TK_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
   c->stats.start_radius = r0;
 
   Job job;
+  if (estimated) {
+    job.r_dev = reinterpret_cast<const float*>(sc + SC_QUANTILE);
+    job.r_host = &c->stats.start_radius;
+  }
   job.queries = c->pts.as<float4>();
   job.n_queries = nq;
   job.q_begin = q_begin;
@@ -677,6 +749,14 @@ int tknn_set_option(tknn_ctx* c, int key, int64_t value) {
       if (value != 0 && (value < 4 || value > 21)) return fail(c, TKNN_EINVAL, "morton bits per axis must be 0 (auto) or in [4, 21]");
       c->morton_bits = (int)value;
       return TKNN_OK;
+    case TKNN_OPT_SPECULATIVE_MAX:
+      if (value < 0 || value > (int64_t)1 << 30) return fail(c, TKNN_EINVAL, "speculative maximum outside [0, 2^30]");
+      c->speculative_max = (int)value;
+      return TKNN_OK;
+    case TKNN_OPT_CURVE:
+      if (value != 0 && value != 1) return fail(c, TKNN_EINVAL, "curve must be 0 (Hilbert) or 1 (Morton)");
+      c->curve = value == 0 ? 1 : 0;  // internal: 1 = Hilbert
+      return TKNN_OK;
     case TKNN_OPT_FILE_ORDER_CHUNKS:
       if (value < 1 || value > 64) return fail(c, TKNN_EINVAL, "file-order chunks outside [1, 64]");
       c->file_order_chunks = (int)value;
@@ -783,7 +863,8 @@ int tknn::host::build_core(tknn_ctx* c, const float* xyz, uint64_t n, int dim, i
   TK_B(ensure(c, vals_b, n * sizeof(uint32_t)));
   const int mbits = c->morton_bits > 0 ? c->morton_bits : auto_morton_bits(n);
   lbvh::morton_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, n, dim, stride_floats, sc + SC_BOUNDS, mbits,
-                                                                             keys_a.as<uint64_t>(), vals_a.as<uint32_t>());
+                                                                             c->curve ? hilbert_levels(n, mbits) : 0, keys_a.as<uint64_t>(),
+                                                                             vals_a.as<uint32_t>());
   ++launches;
   TK_BC(cudaEventRecord(c->ev[3], st));
 
@@ -867,6 +948,7 @@ int tknn::host::build_core(tknn_ctx* c, const float* xyz, uint64_t n, int dim, i
   S.n_leaves = m;
   S.n_nodes = m - 1;
   c->built_morton_bits = mbits;
+  c->built_curve = c->curve ? hilbert_levels(n, mbits) : 0;
   c->has_dup_leaves = dupleaf != 0;
   S.build_launches = (uint32_t)launches;
   c->n = n;
@@ -916,7 +998,10 @@ int tknn_estimate_start_radius(tknn_ctx* c, int k, float* radius_out) {
                                                                      (unsigned long long)c->n);
   ScopedDevice sd(c->device);
   int launches = 0;
-  return estimate_radius(c, c->pts.as<float4>(), 0, c->n, nullptr, 1, k, radius_out, &launches);
+  TK_TRY(estimate_radius_device(c, c->pts.as<float4>(), 0, c->n, nullptr, 1, k, &launches));
+  TK_CUDA(c, cudaMemcpyAsync(radius_out, c->scalars.as<uint32_t>() + SC_QUANTILE, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  TK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return TKNN_OK;
 }
 
 int tknn_query(tknn_ctx* c, const float* queries, uint64_t nq, int dim, int stride_floats, const int32_t* self_ids,
@@ -984,7 +1069,7 @@ int tknn_query(tknn_ctx* c, const float* queries, uint64_t nq, int dim, int stri
   TK_BC(cudaMemsetAsync(sc + SC_ERROR, 0, 2 * sizeof(uint32_t), st));
   const int qbits = c->built_morton_bits;
   lbvh::morton_kernel<<<blocks_for(nq, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_q, nq, dim, stride_floats, sc + SC_BOUNDS, qbits,
-                                                                              keys_a.as<uint64_t>(), vals_a.as<uint32_t>());
+                                                                              c->built_curve, keys_a.as<uint64_t>(), vals_a.as<uint32_t>());
   ++launches;
   bool q_in_b = false;
   launches += rsort::sort_pairs(keys_a.as<uint64_t>(), vals_a.as<uint32_t>(), keys_b.as<uint64_t>(), vals_b.as<uint32_t>(), nq,
@@ -1020,13 +1105,18 @@ int tknn_query(tknn_ctx* c, const float* queries, uint64_t nq, int dim, int stri
   float r0 = start_radius;
   // a query set can hold fewer than k reachable neighbours only through self exclusion / radius caps
   const bool may_underfill = (uint64_t)k > c->n - (self_ids ? 1 : 0);
+  bool estimated = false;
   if (!(r0 > 0.0f)) {
     if (init_radius2 || may_underfill) r0 = INFINITY;
-    else TK_B(estimate_radius(c, qpts.as<float4>(), 0, nq, d_sid_sorted, 0, k, &r0, &launches));
+    else { TK_B(estimate_radius_device(c, qpts.as<float4>(), 0, nq, d_sid_sorted, 0, k, &launches)); estimated = true; }
   }
   TK_BC(cudaEventRecord(c->ev[1], st));
   c->stats.start_radius = r0;
   Job job;
+  if (estimated) {
+    job.r_dev = reinterpret_cast<const float*>(sc + SC_QUANTILE);
+    job.r_host = &c->stats.start_radius;
+  }
   job.queries = qpts.as<float4>();
   job.self_ids = d_sid_sorted;
   job.query_r2 = d_r2_sorted;
@@ -1297,7 +1387,7 @@ int tknn_morton_codes(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int st
   TK_B(ensure(c, dob, sizeof(ob)));
   TK_BC(cudaMemcpyAsync(dob.p, ob, sizeof(ob), cudaMemcpyHostToDevice, st));
   lbvh::morton_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, n, dim, stride_floats, dob.as<uint32_t>(), 21,
-                                                                             d_keys, vals.as<uint32_t>());
+                                                                             0, d_keys, vals.as<uint32_t>());
   TK_BC(cudaGetLastError());
   if (!out_dev) TK_BC(cudaMemcpyAsync(codes_out, d_keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   TK_BC(cudaStreamSynchronize(st));

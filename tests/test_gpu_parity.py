@@ -493,18 +493,24 @@ def test_warp_per_query_kernel_every_round(oracle, cloud, k):
         assert t.stats()["rounds"] >= 2
 
 
+@pytest.mark.parametrize("spec", [0, 1 << 20])
 @pytest.mark.parametrize("wmax", [0, 49152, 1 << 30])
-def test_round_kernels_agree(oracle, wmax):
+def test_round_kernels_agree(oracle, wmax, spec):
     """The three round kernels (cooperative, thread-per-query, warp-per-query) are interchangeable: the
-    result does not depend on which of them a round ran on."""
+    result does not depend on which of them a round ran on — nor on whether round 2 was launched speculatively as the
+    final round (TKNN_OPT_SPECULATIVE_MAX; with the warp kernel allowed for every round size it then covers ALL
+    leftovers, so the search ends after two rounds) or the host waited for the count and kept doubling."""
     from owlraytracing_b200 import TrueKNN
 
     x = datasets.lidar_like(120_000, seed=8)
     ref = oracle.knn_kdtree(x, 12)
-    with TrueKNN(0, warp_round_max=wmax) as t:
+    with TrueKNN(0, warp_round_max=wmax, speculative_max=spec) as t:
         idx, dist = t.build(x).search(12, 0.02)                   # many rounds: 0.02 m against a 200 m scene
-        assert_knn_equal(idx, dist, *ref, f"warp_round_max={wmax}")
-        assert t.stats()["rounds"] >= 4
+        assert_knn_equal(idx, dist, *ref, f"warp_round_max={wmax} speculative_max={spec}")
+        assert t.stats()["rounds"] >= (2 if (spec and wmax == 1 << 30) else 4)
+        idx, dist = t.search(12)                                  # estimated radius: read from the device by round 1
+        assert_knn_equal(idx, dist, *ref, f"auto radius, warp_round_max={wmax} speculative_max={spec}")
+        assert t.stats()["start_radius"] > 0 and t.stats()["start_radius"] == pytest.approx(t.estimate_start_radius(12))
         if wmax == 0:
             t.set_option("counters", 1)
             t.search(12)

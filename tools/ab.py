@@ -1,6 +1,7 @@
 """A/B of library variants on one GPU: same workload, one subprocess per libtrueknn build (TKNN_LIB_PATH).
 
-    python tools/ab.py cfg2|cfg3|cfg4|cfg1 lib1.so lib2.so ...        (paths relative to owlraytracing_b200/lib/)
+    python tools/ab.py cfg2|cfg3|cfg4|cfg1 lib1.so lib2.so:curve=1 ...   (paths relative to owlraytracing_b200/lib/;
+                                                                        optional tknn_set_option settings after ':')
 
 Per variant: best-of-5 search_ms through tknn_search_shard (compact rows, device outputs: the bench's timed call), the
 per-round kernel times, build phases, and a checksum of the result (all variants must agree; the first is compared
@@ -23,7 +24,8 @@ def child(which):
     from owlraytracing_b200 import TrueKNN, datasets
 
     n, k, cloud, seed = CFG[which]
-    t = TrueKNN(0)
+    opts = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in os.environ.get("TKNN_AB_OPTS", "").split(",") if kv}
+    t = TrueKNN(0, **opts)
     t.set_stream(torch.cuda.current_stream().cuda_stream)
     if cloud == "uniform":
         x = torch.empty((n, 3), dtype=torch.float32, device="cuda")
@@ -53,7 +55,7 @@ def child(which):
     t.set_option("counters", 1)
     t.search_shard(k, 0, 1, out=out)
     c = t.stats()
-    print(json.dumps({"lib": os.path.basename(os.environ.get("TKNN_LIB_PATH", "default")), "workload": which,
+    print(json.dumps({"lib": os.path.basename(os.environ.get("TKNN_LIB_PATH", "default")), "opts": opts, "workload": which,
                       "search_ms": round(best["search_ms"], 4), "estimate_ms": round(best["estimate_ms"], 4),
                       "kernel_ms": [round(v, 4) for v in best["kernel_ms"]], "round_queries": best["round_queries"],
                       "qps_M": round(n / best["search_ms"] / 1e3, 1), "build_ms": round(b["build_ms"], 4),
@@ -67,7 +69,8 @@ if __name__ == "__main__":
         child(sys.argv[2])
     else:
         which, libs = sys.argv[1], sys.argv[2:] or ["libtrueknn.so"]
-        for lib in libs:
-            env = dict(os.environ, TKNN_LIB_PATH=os.path.join(ROOT, "owlraytracing_b200", "lib", lib))
+        for spec in libs:
+            lib, _, o = spec.partition(":")     # "lib.so:option=value,option=value"
+            env = dict(os.environ, TKNN_LIB_PATH=os.path.join(ROOT, "owlraytracing_b200", "lib", lib), TKNN_AB_OPTS=o)
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", which], env=env, capture_output=True, text=True, timeout=900)
             print(r.stdout.strip().splitlines()[-1] if r.returncode == 0 and r.stdout.strip() else json.dumps({"lib": lib, "rc": r.returncode, "err": r.stderr[-600:]}), flush=True)
