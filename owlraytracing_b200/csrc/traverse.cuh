@@ -188,22 +188,38 @@ constexpr int COOP_MAX_LANES = TKNN_COOP_MAX_LANES;
 // (32 consecutive keys of one slot) stay conflict-free too.
 constexpr int KLS = COOP_MAX_LANES > 0 ? 33 : 32;
 
+// Returns the key left in the slot that was filled, i.e. the list's new LAST entry — the new worst once the list is
+// full — so the caller keeps the bound and the worst index in registers instead of re-reading them.
 template <int S = 32>
-__device__ __forceinline__ void list_insert(uint64_t* L, int& cnt, int k, uint64_t key) {
+__device__ __forceinline__ uint64_t list_insert(uint64_t* L, int& cnt, int k, uint64_t key) {
   uint64_t* p = L + (cnt < k ? cnt + 1 : k) * S;  // the slot being filled
   if (cnt < k) ++cnt;
-  for (;;) {
+  uint64_t tail;
+  {
     // four independent loads in flight: one shared-memory latency per four steps.  Slots below the
     // sentinel (at most three) are never used: the walk stops at the sentinel; they lie inside this
     // warp's own staging area, so the reads are in bounds.
     const uint64_t a = *(p - S), b = *(p - 2 * S), c = *(p - 3 * S), d = *(p - 4 * S);
-    if (a <= key) { *p = key; return; }
+    if (a <= key) { *p = key; return key; }
     *p = a;
-    if (b <= key) { *(p - S) = key; return; }
+    tail = a;
+    if (b <= key) { *(p - S) = key; return tail; }
     *(p - S) = b;
-    if (c <= key) { *(p - 2 * S) = key; return; }
+    if (c <= key) { *(p - 2 * S) = key; return tail; }
     *(p - 2 * S) = c;
-    if (d <= key) { *(p - 3 * S) = key; return; }
+    if (d <= key) { *(p - 3 * S) = key; return tail; }
+    *(p - 3 * S) = d;
+    p -= 4 * S;
+  }
+  for (;;) {
+    const uint64_t a = *(p - S), b = *(p - 2 * S), c = *(p - 3 * S), d = *(p - 4 * S);
+    if (a <= key) { *p = key; return tail; }
+    *p = a;
+    if (b <= key) { *(p - S) = key; return tail; }
+    *(p - S) = b;
+    if (c <= key) { *(p - 2 * S) = key; return tail; }
+    *(p - 2 * S) = c;
+    if (d <= key) { *(p - 3 * S) = key; return tail; }
     *(p - 3 * S) = d;
     p -= 4 * S;
   }
@@ -373,6 +389,22 @@ __device__ __forceinline__ uint32_t filter4(const float* sx, int j0, float2 qx, 
   return m;
 }
 
+// Insert loop of the dense kernel: 1 (default) = every lane walks its own survivors and the warp reconverges once behind
+// the loop; 0 = warp-voted loop, one candidate per lane per iteration (round 1's form).  Measured (profiles/
+// r2_ab_insert.jsonl): cfg2 7.53 -> 7.35 ms, cfg3 48.95 -> 45.79 ms: the vote, its divergence check and the
+// reconvergence points cost ~10 of the ~100 warp instructions of an iteration.
+#ifndef TKNN_INSERT_LOOP
+#define TKNN_INSERT_LOOP 1
+#endif
+// Worst entry of a full ascending list: 2 (default) = list_insert hands back the new tail, so the bound is updated from
+// registers, and the stored worst key is re-read only when a candidate TIES the bound (its index then decides);
+// 0 = re-read the tail slot before and after every insert (round 1); 1 = also keep the worst index in a register
+// (55 registers instead of 47: 36 instead of 40 resident warps).  cfg2 (profiles/r2_ab_insert.jsonl, r2_ab_wreg2.jsonl):
+// 0: 7.33 ms, 1: 7.65 ms, 2: 7.30 ms.
+#ifndef TKNN_WORST_REG
+#define TKNN_WORST_REG 2
+#endif
+
 // VARIANT: 0 = exact filter, 1 = conservative pre-filter (audited option), 2 = exact filter + index-aware
 // tie pruning (chosen by the host when the build found leaves of coincident points).
 // HEAP: k > LIST_MAX_K (compile-time, so the small-k kernel does not carry the heap code).
@@ -421,6 +453,7 @@ static __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
     if (valid && P.query_r2) r2 = fminf(r2, P.query_r2[qpos]);
     float bound = valid ? r2 : -1.0f;  // d2 >= 0 > -1: an idle lane never wants anything
     int cnt = 0;
+    int widx = 0x7fffffff;             // index of the list's worst entry once it is full (TKNN_WORST_REG)
     if (MODE == MODE_KNN) H[0] = 0;    // sentinel of this lane's k-list
     // group-local origin and this lane's pre-filter constants
     float ax, ay, az, qq;
@@ -523,6 +556,38 @@ static __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
                 mask |= filter4(soa, j0, qx2, qy2, qz2, bound) << j0;
             }
             // insert: only lanes with survivors do work; the bound tightens as they go
+#if TKNN_INSERT_LOOP == 1
+            // every lane walks its own survivors; the warp reconverges once, behind the loop (no vote per candidate)
+            while (mask) {
+              const int j = __ffs(mask) - 1;
+              mask &= mask - 1u;
+              const float4 p = stage[j];
+              const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+              const int pid = __float_as_int(p.w);
+              if (pid != self && d <= bound) {
+                const uint64_t key = make_key(d, pid);
+                if (!HEAP && TKNN_WORST_REG == 2) {
+                  // d <= bound holds: the key beats the worst entry unless it TIES its distance with a higher index
+                  if (cnt < k || d < bound || pid < key_idx(kl_worst<S>(H, k, heap))) {
+                    const uint64_t tail = list_insert<S>(H, cnt, k, key);
+                    if (cnt == k) bound = key_d2(tail);
+                    if (COUNT) c_ins += 1;
+                  }
+                } else if (!HEAP && TKNN_WORST_REG) {
+                  // (d, pid) < (bound, widx): the worst entry's key lives in registers (bound = its d2)
+                  if (cnt < k || d < bound || pid < widx) {
+                    const uint64_t tail = list_insert<S>(H, cnt, k, key);
+                    if (cnt == k) { bound = key_d2(tail); widx = key_idx(tail); }
+                    if (COUNT) c_ins += 1;
+                  }
+                } else if (cnt < k || key < kl_worst<S>(H, k, heap)) {
+                  kl_insert<true, S>(H, cnt, k, key, heap);
+                  if (cnt == k) bound = key_d2(kl_worst<S>(H, k, heap));
+                  if (COUNT) c_ins += 1;
+                }
+              }
+            }
+#else
             for (;;) {
               unsigned pend = __ballot_sync(FULL_MASK, mask != 0u);
               if (pend == 0u) break;
@@ -562,7 +627,13 @@ static __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
                 const int pid = __float_as_int(p.w);
                 if (pid != self && d <= bound) {
                   const uint64_t key = make_key(d, pid);
-                  if (cnt < k || key < kl_worst<S>(H, k, heap)) {
+                  if (!HEAP && TKNN_WORST_REG) {
+                    if (cnt < k || d < bound || pid < widx) {
+                      const uint64_t tail = list_insert<S>(H, cnt, k, key);
+                      if (cnt == k) { bound = key_d2(tail); widx = key_idx(tail); }
+                      if (COUNT) c_ins += 1;
+                    }
+                  } else if (cnt < k || key < kl_worst<S>(H, k, heap)) {
                     kl_insert<true, S>(H, cnt, k, key, heap);
                     if (cnt == k) bound = key_d2(kl_worst<S>(H, k, heap));
                     if (COUNT) c_ins += 1;
@@ -570,6 +641,7 @@ static __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
                 }
               }
             }
+#endif
           }
           __syncwarp();
         }
