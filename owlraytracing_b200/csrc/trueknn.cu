@@ -292,7 +292,10 @@ int run_rounds(tknn_ctx* c, const Job& job, int* launches_io) {
     const bool sparse = trav::sparse_smem(job.k) <= 200 * 1024 &&
                         (job.force_sparse || (c->sparse_divisor > 0 && queue != nullptr && round > 0 &&
                                               active * (uint64_t)c->sparse_divisor <= n0));
-    const bool tiny = c->warp_round_max > 0 && active <= (uint64_t)c->warp_round_max;
+    // one warp per query: small rounds; four times further for k > 24, where a private heap per THREAD is slow
+    // (cfg3, 51 725 leftover queries: 3.6 ms on the thread-per-query kernel, profiles/r2_ab_opts.jsonl)
+    const bool tiny = c->warp_round_max > 0 &&
+                      active <= (uint64_t)c->warp_round_max * (job.k > trav::LIST_MAX_K ? 4u : 1u);
     if (tiny) TK_TRY(launch_traverse_warp(c, P));
     else if (sparse) TK_TRY(launch_traverse_sparse(c, P));
     else TK_TRY(launch_traverse<trav::MODE_KNN>(c, P));

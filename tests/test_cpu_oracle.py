@@ -302,3 +302,47 @@ def test_fast_ingest_matches_grammar_and_writer_round_trips(oracle, tmp_path):
     assert (back[:, 2].astype(np.float32) == dist.reshape(-1)).all()
     write_neighbours(str(tmp_path / "nn"), idx, dist, binary=True)
     assert (np.fromfile(str(tmp_path / "nn.idx.i32"), np.int32).reshape(idx.shape) == idx).all()
+
+
+def test_read_points_reports_the_capacity_it_needs(tmp_path):
+    """the grammar consumes the LAST line read whole (hostCode.cpp:92), so a file with many floats per line
+    yields more than n rows; tknn_read_points then names the capacity a retry needs and the Python / C++ hosts retry."""
+    from owlraytracing_b200 import read_points, read_points_fast
+
+    pts = np.arange(300, dtype=np.float32).reshape(100, 3)
+    one_line = tmp_path / "one_line.txt"
+    one_line.write_text(" ".join(repr(float(v)) for v in pts.reshape(-1)) + "\n")   # all 300 floats on one line
+    want = read_points(str(one_line), 10, 3)            # the reference reads the whole line: 100 points, not 10
+    assert want.shape == (100, 3)
+    got = read_points_fast(str(one_line), 10, 3)
+    assert (got == want).all()
+    L = _lib.load()
+    out = np.empty((18, 3), np.float32)
+    m = ctypes.c_uint64(0)
+    rc = L.tknn_read_points(str(one_line).encode(), 10, 3, ctypes.c_void_p(out.ctypes.data), 18, ctypes.byref(m))
+    assert rc == _lib.EINVAL and m.value == 100       # too small: the row count it needs comes back
+    four = tmp_path / "four_per_line.txt"
+    four.write_text("\n".join(",".join(repr(float(v)) for v in row) for row in pts.reshape(-1, 12)) + "\n")
+    assert (read_points_fast(str(four), 7, 3) == read_points(str(four), 7, 3)).all()
+
+
+def test_bench_cpu_arm_sampling_is_coherent_and_uses_all_cores(oracle):
+    """bench.py's CPU arm: runs of consecutive tree positions (spatially coherent like the GPU's order), answers equal to
+    the plain query path, and every core in use even when the launcher exported OMP_NUM_THREADS=1 (torchrun does)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    pos = bench._coherent_positions(1_000_000, 50_000, 3)
+    assert pos.shape == (50_000,) and len(np.unique(pos)) == 50_000 and pos.min() >= 0 and pos.max() < 1_000_000
+    assert (np.diff(pos.reshape(-1, 4096)[:, :], axis=1) == 1).all() if pos.size % 4096 == 0 else True
+    assert (bench._coherent_positions(1000, 5000, 0) < 1000).all()
+    x = datasets.uniform(60_000, seed=3)
+    t = oracle.KdTree(x, leaf=8)
+    ids, idx, dist = t.query_positions(bench._coherent_positions(60_000, 9_000, 1), 7)
+    ri, rd = t.query(x[ids], 7, self_ids=ids)
+    assert (idx == ri).all() and (dist == rd).all()
+    t.close()
+    oracle.set_num_threads(os.cpu_count())
+    assert oracle.num_threads() == os.cpu_count()

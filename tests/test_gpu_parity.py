@@ -531,3 +531,45 @@ def test_committed_golden_vectors(knn, case):
     # and from a tiny start radius (many rounds), same answer
     idx2, dist2 = knn.search(k, 1e-4)
     assert (idx2 == g[f"{case}_idx"]).all() and (dist2 == g[f"{case}_dist"]).all()
+
+
+def test_non_finite_queries_are_rejected(knn):
+    """tknn_query with a NaN / inf coordinate returns TKNN_EINVAL instead of a silent row of -1."""
+    from owlraytracing_b200 import TrueKNNError
+
+    x = datasets.uniform(5000, seed=4)
+    knn.build(x)
+    q = datasets.uniform(200, seed=5)
+    idx, dist = knn.query(q, 5)
+    assert (idx >= 0).all()
+    for bad in (np.nan, np.inf):
+        qb = q.copy()
+        qb[17, 1] = bad
+        with pytest.raises(TrueKNNError) as e:
+            knn.query(qb, 5)
+        assert e.value.code == 1
+    idx2, _ = knn.query(q, 5)          # the context stays usable
+    assert (idx2 == idx).all()
+
+
+def test_shared_memory_bandwidth_probe(knn):
+    """bench.py's roofline denominator: conflict-free LDS.128 delivers the 128 B/clk/SM crossbar (about 37 TB/s on a B200),
+    warp-broadcast LDS.128 about twice that in bytes delivered to lanes."""
+    m = knn.measure_smem_bandwidth()
+    assert 20_000 < m["smem_conflict_free_gbs"] < 45_000
+    assert m["smem_broadcast_gbs"] > m["smem_conflict_free_gbs"]
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_space_filling_curve_is_result_invariant(oracle, curve):
+    """TKNN_OPT_CURVE: Hilbert (default) or Morton keys order the points and the tree's children differently; the k
+    nearest neighbours do not depend on it, and the Hilbert order needs fewer node visits and point tests per query."""
+    from owlraytracing_b200 import TrueKNN
+
+    x = datasets.lidar_like(150_000, seed=12)
+    ref = oracle.knn_kdtree(x, 10)
+    with TrueKNN(0, curve=curve, counters=1) as t:
+        idx, dist = t.build(x).search(10)
+        assert_knn_equal(idx, dist, *ref, f"curve={curve}")
+        qi, qd = t.query(x[:5000], 10, self_ids=np.arange(5000, dtype=np.int32))   # queries are coded on the same curve
+        assert_knn_equal(qi, qd, ref[0][:5000], ref[1][:5000], f"query, curve={curve}")
