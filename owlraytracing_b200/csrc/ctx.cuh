@@ -53,6 +53,7 @@ struct tknn_ctx {
   bool has_dup_leaves = false; // the build found a leaf of coincident points => tie-pruning kernel variant
   int built_morton_bits = 21; // what the current BVH was built with (queries are coded the same way)
   int curve = 1;              // space-filling curve of the next build: 1 = Hilbert (default), 0 = Morton
+  int curve_levels = 0;       // > 0: Hilbert levels forced (experiments); 0 = ceil(log2 n / 3) + 2
   int built_curve = 0;        // Hilbert levels the current BVH's keys were made with (0 = Morton): queries are coded alike
   int output_chunks = 4;  // host-output pipelining: slices whose D2H overlaps the next slice's search (1 = off)
   int file_order_chunks = 4;  // same for tknn_search (file-order rows): slices by original index (1 = off)

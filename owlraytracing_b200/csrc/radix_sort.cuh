@@ -79,7 +79,8 @@ static __global__ void __launch_bounds__(RADIX) scan_histogram_kernel(uint32_t* 
 
 // Lanes holding the same 8-bit digit.  Eight ballots (one per digit bit) instead of `match.any`: the
 // instruction loops over the distinct values in the warp (~30 of them for 8-bit digits) and its latency
-// sat on the ranking loop's critical path — 38 % of the pass's stall samples (profiles/r1_sort_v8_*).
+// sat on the ranking loop's critical path — 38 % of the pass's stall samples (round-1 capture; the kernel as it is now:
+// profiles/r1_sort_v8_onesweep_ncu_summary.json, profiles/r2_build_onesweep_kernel_ncu_summary.json + _regions.txt).
 __device__ __forceinline__ uint32_t match_digit(uint32_t d) {
   uint32_t peers = FULL_MASK;
 #pragma unroll
@@ -92,7 +93,10 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d) {
 }
 
 // One onesweep pass over digit `shift / 8`.
-static __global__ void __launch_bounds__(THREADS, 3)
+#ifndef TKNN_SORT_MINBLOCKS
+#define TKNN_SORT_MINBLOCKS 3
+#endif
+static __global__ void __launch_bounds__(THREADS, TKNN_SORT_MINBLOCKS)
     onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                     uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint64_t n, int shift,
                     const uint32_t* __restrict__ bin_offset, uint32_t* status, uint32_t* tile_counter) {

@@ -423,7 +423,8 @@ int auto_morton_bits(uint64_t n) {
 }
 
 // Hilbert levels of the key kernel (lbvh.cuh: morton_kernel): two levels below the one where a cell holds one point
-int hilbert_levels(uint64_t n, int bits) {
+int hilbert_levels(uint64_t n, int bits, int forced = 0) {
+  if (forced > 0) return std::max(2, std::min(bits, forced));
   int lg = 0;
   while (((uint64_t)1 << lg) < n) ++lg;
   return std::max(2, std::min(bits, (lg + 2) / 3 + 2));
@@ -757,8 +758,10 @@ int tknn_set_option(tknn_ctx* c, int key, int64_t value) {
       c->speculative_max = (int)value;
       return TKNN_OK;
     case TKNN_OPT_CURVE:
-      if (value != 0 && value != 1) return fail(c, TKNN_EINVAL, "curve must be 0 (Hilbert) or 1 (Morton)");
-      c->curve = value == 0 ? 1 : 0;  // internal: 1 = Hilbert
+      if (value != 0 && value != 1 && !(value >= 101 && value <= 121))
+        return fail(c, TKNN_EINVAL, "curve must be 0 (Hilbert), 1 (Morton) or 100 + L (Hilbert on exactly L levels)");
+      c->curve = value == 1 ? 0 : 1;  // internal: 1 = Hilbert
+      c->curve_levels = value > 100 ? (int)value - 100 : 0;
       return TKNN_OK;
     case TKNN_OPT_FILE_ORDER_CHUNKS:
       if (value < 1 || value > 64) return fail(c, TKNN_EINVAL, "file-order chunks outside [1, 64]");
@@ -866,7 +869,7 @@ int tknn::host::build_core(tknn_ctx* c, const float* xyz, uint64_t n, int dim, i
   TK_B(ensure(c, vals_b, n * sizeof(uint32_t)));
   const int mbits = c->morton_bits > 0 ? c->morton_bits : auto_morton_bits(n);
   lbvh::morton_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, n, dim, stride_floats, sc + SC_BOUNDS, mbits,
-                                                                             c->curve ? hilbert_levels(n, mbits) : 0, keys_a.as<uint64_t>(),
+                                                                             c->curve ? hilbert_levels(n, mbits, c->curve_levels) : 0, keys_a.as<uint64_t>(),
                                                                              vals_a.as<uint32_t>());
   ++launches;
   TK_BC(cudaEventRecord(c->ev[3], st));
@@ -951,7 +954,7 @@ int tknn::host::build_core(tknn_ctx* c, const float* xyz, uint64_t n, int dim, i
   S.n_leaves = m;
   S.n_nodes = m - 1;
   c->built_morton_bits = mbits;
-  c->built_curve = c->curve ? hilbert_levels(n, mbits) : 0;
+  c->built_curve = c->curve ? hilbert_levels(n, mbits, c->curve_levels) : 0;
   c->has_dup_leaves = dupleaf != 0;
   S.build_launches = (uint32_t)launches;
   c->n = n;
