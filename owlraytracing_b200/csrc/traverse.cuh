@@ -1027,15 +1027,28 @@ static __global__ void __launch_bounds__(1024) radius_quantile_kernel(const floa
       if (shift == 24 && u > 0u && u < 0x7f800000u) atomicMax(&s_maxpos, u);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t acc = 0;
-      int b = 0;
-      for (; b < 255; ++b) {
-        if (acc + s_hist[b] > want) break;
-        acc += s_hist[b];
+    if (threadIdx.x < 32) {  // warp 0: lane l owns bins 8 l .. 8 l + 7; the bin whose cumulative count passes `want`
+      uint32_t mine = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mine += s_hist[threadIdx.x * 8 + j];
+      uint32_t inc = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL_MASK, inc, o);
+        if ((int)threadIdx.x >= o) inc += t;
       }
-      s_prefix = prefix | ((uint32_t)b << shift);
-      s_want = want - acc;
+      const uint32_t before = inc - mine;
+      const int owner = __ffs(__ballot_sync(FULL_MASK, inc > want)) - 1;  // first lane whose inclusive sum passes it
+      if ((int)threadIdx.x == (owner < 0 ? 31 : owner)) {
+        uint32_t acc = before;
+        int b = threadIdx.x * 8;
+        for (; b < (int)threadIdx.x * 8 + 7; ++b) {
+          if (acc + s_hist[b] > want) break;
+          acc += s_hist[b];
+        }
+        s_prefix = prefix | ((uint32_t)b << shift);
+        s_want = want - acc;
+      }
     }
     __syncthreads();
     prefix = s_prefix;
