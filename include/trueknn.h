@@ -79,6 +79,9 @@ enum {
   ,TKNN_OPT_SPECULATIVE_MAX = 17 /* searches of at most this many queries run without a host decision between their launches:
                                   round 2 is launched as the final round before the host knows how many queries round 1 left
                                   (default 2^20; 0 = always wait for the count) */
+  ,TKNN_OPT_SPARSE_TEAM = 18    /* sparse rounds (more than WARP_ROUND_MAX leftover queries, fewer than n / SPARSE_DIVISOR): 0 (default)
+                                  = one thread per query; 4, 8, 16 = a team of that many lanes shares one traversal (measured
+                                  slower: cfg2's 97 478 leftovers 0.45 ms with threads, 0.78 / 0.65 / 0.63 ms with teams) */
   ,TKNN_OPT_SPARSE_DIVISOR = 9 /* rounds >= 2 with fewer than n/divisor active queries run the
                                   thread-per-query kernel (default 8; 0 = never)                  */
 };

@@ -46,6 +46,7 @@ struct tknn_ctx {
   int keep_scratch = 1;
   int sparse_divisor = 8;
   int warp_round_max = 49152;  // rounds with at most this many active queries run one warp per query (0 = never)
+  int sparse_team = 0;         // lanes per query in sparse rounds: 0 = the thread-per-query kernel (default: fastest), 4 / 8 / 16 = teams
   int speculative_max = 1 << 20;  // searches of at most this many queries launch round 2 without a host decision (0 = never)
   int approx_filter = 0;
   int tie_pruning = 0;        // 0 = auto (on when the build saw leaves of coincident points), 1 = on, 2 = off

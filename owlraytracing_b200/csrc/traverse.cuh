@@ -401,6 +401,11 @@ __device__ __forceinline__ uint32_t filter4(const float* sx, int j0, float2 qx, 
 // 0 = re-read the tail slot before and after every insert (round 1); 1 = also keep the worst index in a register
 // (55 registers instead of 47: 36 instead of 40 resident warps).  cfg2 (profiles/r2_ab_insert.jsonl, r2_ab_wreg2.jsonl):
 // 0: 7.33 ms, 1: 7.65 ms, 2: 7.30 ms.
+// 1: the two internal-child votes as one REDUX.OR and the near-first majority as one REDUX.SUM.  Measured neutral (cfg2 round 1
+// 6.630 vs 6.632 ms, cfg3 44.43 vs 44.44 ms, profiles/r2_ab_team.jsonl): off.
+#ifndef TKNN_REDUX_VOTES
+#define TKNN_REDUX_VOTES 0
+#endif
 #ifndef TKNN_WORST_REG
 #define TKNN_WORST_REG 2
 #endif
@@ -648,15 +653,26 @@ static __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
       }
 
       // ---- internal children, voted against the (tightened) bounds ----
+#if TKNN_REDUX_VOTES
+      // one warp reduction for both children (REDUX.OR) instead of two votes, one (REDUX.SUM) for the near-first majority
+      const unsigned want = __reduce_or_sync(FULL_MASK, (d0 <= bound ? 1u : 0u) | (d1 <= bound ? 2u : 0u));
+      bool w0 = (cnt0 == 0) && (want & 1u);
+      bool w1 = (cnt1 == 0) && (want & 2u);
+#else
       bool w0 = (cnt0 == 0) && __any_sync(FULL_MASK, d0 <= bound);
       bool w1 = (cnt1 == 0) && __any_sync(FULL_MASK, d1 <= bound);
+#endif
       if (TIES && (w0 || w1)) {
         const int2 mi = __ldg(&P.node_min_idx[node]);
         if (w0) w0 = child_wanted<MODE, S>(d0, bound, cnt, k, H, heap, mi.x);
         if (w1) w1 = child_wanted<MODE, S>(d1, bound, cnt, k, H, heap, mi.y);
       }
       if (w0 && w1) {
+#if TKNN_REDUX_VOTES
+        const bool far0 = __reduce_add_sync(FULL_MASK, (d1 < d0 ? 1 : 0) - (d0 < d1 ? 1 : 0)) > 0;
+#else
         const bool far0 = __popc(__ballot_sync(FULL_MASK, d1 < d0)) > __popc(__ballot_sync(FULL_MASK, d0 < d1));
+#endif
         const int nearc = far0 ? ref1 : ref0, farc = far0 ? ref0 : ref1;
         if (sp < STACK_DEPTH) {
           if (lane == 0) stack[sp] = farc;
@@ -844,47 +860,61 @@ static __global__ void __launch_bounds__(SPARSE_THREADS) traverse_sparse_kernel(
 // decisions are scalar (one query), same strict pruning, same (d2, index) keys => same results.
 // Unresolved queries set their bit in P.unresolved with atomicOr: the host zeroes the words first.
 // ------------------------------------------------------------------------------------------------
-constexpr int WQ_WARPS = 4;  // queries per block
+constexpr int WQ_WARPS = 4;  // warps per block
 
-__host__ __device__ inline size_t warpq_smem(int k) {
-  return (size_t)WQ_WARPS * ((size_t)k * sizeof(uint64_t) + STACK_DEPTH * sizeof(int));
+// T = lanes per query: 32 (one warp per query: tiny rounds) or a TEAM of 4 / 8 / 16 lanes, 32 / T queries per warp
+// (TKNN_OPT_SPARSE_TEAM, for sparse rounds).  A team loads its node and its leaf chunk coalesced, tests T points per step,
+// and its k-list is one ascending array in shared memory shifted cooperatively; teams of one warp follow different paths,
+// so every warp-level primitive below is masked to the team (independent thread scheduling), nothing is block-wide.
+// MEASURED (profiles/r2_ab_team.jsonl): for sparse rounds the teams LOSE to the thread-per-query kernel — cfg2's 97 478
+// leftover queries: 0.447 ms with threads, 0.78 / 0.65 / 0.63 ms with teams of 4 / 8 / 16; cfg4's 568 002: 1.64 vs 3.71 ms —
+// the teams of a warp serialise on their diverging paths and each repeats the node test on all its lanes, while 32
+// private walks keep 32 loads in flight per warp.  So T = 32 serves the tiny rounds and the teams stay an option.
+__host__ __device__ inline size_t warpq_smem(int k, int T = 32) {
+  return (size_t)WQ_WARPS * (32 / T) * ((size_t)k * sizeof(uint64_t) + STACK_DEPTH * sizeof(int));
 }
 
 // inserts `key` into the ascending list L[0, cnt) of capacity k (the largest entry falls off a full list);
-// precondition: cnt < k or key < L[k - 1]; keys are distinct.  All 32 lanes call it together.
-__device__ __forceinline__ void warp_list_insert(uint64_t* L, int& cnt, int k, uint64_t key, int lane) {
+// precondition: cnt < k or key < L[k - 1]; keys are distinct.  All T lanes of the team call it together
+// (tl = lane within the team, tmask = the team's lanes, tshift = its first lane).
+template <int T>
+__device__ __forceinline__ void team_list_insert(uint64_t* L, int& cnt, int k, uint64_t key, int tl, unsigned tmask) {
   int pos = 0;  // entries smaller than key
-  for (int c0 = 0; c0 < cnt; c0 += 32) {
-    const int i = c0 + lane;
+  for (int c0 = 0; c0 < cnt; c0 += T) {
+    const int i = c0 + tl;
     const uint64_t e = i < cnt ? L[i] : ~0ull;
-    pos += __popc(__ballot_sync(FULL_MASK, e < key));
+    pos += __popc(__ballot_sync(tmask, e < key));
   }
   const int n_new = cnt < k ? cnt + 1 : k;
-  // shift [pos, n_new - 1) one slot up, 32 entries at a time from the top: a chunk reads its old values
+  // shift [pos, n_new - 1) one slot up, T entries at a time from the top: a chunk reads its old values
   // (and the last entry of the still untouched chunk below) before it writes
-  for (int c0 = ((n_new - 1) >> 5) << 5; c0 >= ((pos >> 5) << 5); c0 -= 32) {
-    const int i = c0 + lane;
+  for (int c0 = ((n_new - 1) / T) * T; c0 >= (pos / T) * T; c0 -= T) {
+    const int i = c0 + tl;
     const bool moved = i > pos && i < n_new;
     uint64_t prev = 0;
     if (moved) prev = L[i - 1];
-    __syncwarp();
+    __syncwarp(tmask);
     if (moved) L[i] = prev;
     else if (i == pos) L[i] = key;
-    __syncwarp();
+    __syncwarp(tmask);
   }
   cnt = n_new;
 }
 
-template <bool COUNT>
+template <bool COUNT, int T>
 static __global__ void __launch_bounds__(WQ_WARPS * 32) traverse_warp_kernel(const Params P) {
   extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int TEAMS = 32 / T;                 // queries per warp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int team = lane / T, tl = lane % T, tshift = team * T;
+  const unsigned tmask = T == 32 ? FULL_MASK : (((1u << (T & 31)) - 1u) << tshift);
   const int k = P.k;
-  uint64_t* L = reinterpret_cast<uint64_t*>(smem) + (size_t)warp * k;
-  int* stack = reinterpret_cast<int*>(smem + (size_t)WQ_WARPS * k * sizeof(uint64_t)) + warp * STACK_DEPTH;
-  const uint64_t gi = (uint64_t)blockIdx.x * WQ_WARPS + warp;
+  const int slot = warp * TEAMS + team;         // this query's list and stack inside the block
+  uint64_t* L = reinterpret_cast<uint64_t*>(smem) + (size_t)slot * k;
+  int* stack = reinterpret_cast<int*>(smem + (size_t)WQ_WARPS * TEAMS * k * sizeof(uint64_t)) + slot * STACK_DEPTH;
+  const uint64_t gi = ((uint64_t)blockIdx.x * WQ_WARPS + warp) * TEAMS + team;
   const uint64_t n_active = P.n_active_dev ? min((uint64_t)__ldg(P.n_active_dev), P.n_active) : P.n_active;
-  if (gi >= n_active) return;  // the whole warp leaves; the kernel has no block-wide barrier
+  if (gi >= n_active) return;  // the whole team leaves; the kernel has no block-wide barrier
   const uint64_t qpos = P.queue ? (uint64_t)P.queue[gi] : P.q_begin + gi;
   const float4 q = __ldg(&P.queries[qpos]);
   const int row_id = __float_as_int(q.w);
@@ -918,26 +948,30 @@ static __global__ void __launch_bounds__(WQ_WARPS * 32) traverse_warp_kernel(con
         if ((second ? mi.y : mi.x) >= key_idx(worst)) continue;
       }
       if (COUNT) c_tests += lcount;
-      bool pass = false;
-      uint64_t key = 0;
-      if (lane < lcount) {
-        const float4 p = __ldg(&P.pts[(uint64_t)(uint32_t)(second ? ref1 : ref0) + lane]);
-        const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
-        const int pid = __float_as_int(p.w);
-        pass = d <= bound && pid != self;
-        key = make_key(d, pid);
-      }
-      unsigned m = __ballot_sync(FULL_MASK, pass);
-      while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1u;
-        const uint64_t kk = __shfl_sync(FULL_MASK, key, src);
-        if (cnt == k && kk >= worst) continue;
-        warp_list_insert(L, cnt, k, kk, lane);
-        if (COUNT) c_ins += 1;
-        if (cnt == k) {
-          worst = L[k - 1];
-          bound = key_d2(worst);
+      const float4* lp = P.pts + (uint64_t)(uint32_t)(second ? ref1 : ref0);
+#pragma unroll 1
+      for (int j0 = 0; j0 < lcount; j0 += T) {  // T points per step; the bound tightens between steps
+        bool pass = false;
+        uint64_t key = 0;
+        if (j0 + tl < lcount) {
+          const float4 p = __ldg(lp + j0 + tl);
+          const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+          const int pid = __float_as_int(p.w);
+          pass = d <= bound && pid != self;
+          key = make_key(d, pid);
+        }
+        unsigned m = __ballot_sync(tmask, pass) >> tshift;
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1u;
+          const uint64_t kk = __shfl_sync(tmask, key, tshift + src);
+          if (cnt == k && kk >= worst) continue;
+          team_list_insert<T>(L, cnt, k, kk, tl, tmask);
+          if (COUNT) c_ins += 1;
+          if (cnt == k) {
+            worst = L[k - 1];
+            bound = key_d2(worst);
+          }
         }
       }
     }
@@ -951,9 +985,9 @@ static __global__ void __launch_bounds__(WQ_WARPS * 32) traverse_warp_kernel(con
     }
     if (w0 && w1) {
       if (sp < STACK_DEPTH) {
-        if (lane == 0) stack[sp] = swap ? ref0 : ref1;
+        if (tl == 0) stack[sp] = swap ? ref0 : ref1;
         ++sp;
-      } else if (lane == 0) {
+      } else if (tl == 0) {
         atomicOr(P.error, 1u);
       }
       node = swap ? ref1 : ref0;
@@ -964,20 +998,20 @@ static __global__ void __launch_bounds__(WQ_WARPS * 32) traverse_warp_kernel(con
     } else {
       if (sp == 0) break;
       --sp;
-      __syncwarp();
+      __syncwarp(tmask);
       node = stack[sp];
     }
   }
 
   const bool resolved = cnt == k;
-  if (!resolved && P.unresolved && lane == 0) atomicOr(&P.unresolved[gi >> 5], 1u << (unsigned)(gi & 31));
+  if (!resolved && P.unresolved && tl == 0) atomicOr(&P.unresolved[gi >> 5], 1u << (unsigned)(gi & 31));
   if (resolved || P.final_round) {
     const uint64_t row = P.row_mode == 0 ? (uint64_t)(uint32_t)row_id : (P.row_mode == 1 ? qpos - P.q_begin : gi);
     int32_t* io = P.idx_out + row * (uint64_t)k;
     float* dd = P.dist_out + row * (uint64_t)k;
-    if (P.row_mode && P.qid_out && lane == 0) P.qid_out[row] = row_id;
-    __syncwarp();
-    for (int i = lane; i < k; i += 32) {
+    if (P.row_mode && P.qid_out && tl == 0) P.qid_out[row] = row_id;
+    __syncwarp(tmask);
+    for (int i = tl; i < k; i += T) {
       if (i < cnt) {
         const uint64_t e = L[i];
         io[i] = key_idx(e);
@@ -988,7 +1022,7 @@ static __global__ void __launch_bounds__(WQ_WARPS * 32) traverse_warp_kernel(con
       }
     }
   }
-  if (COUNT && P.counters && lane == 0) {
+  if (COUNT && P.counters && tl == 0) {
     atomicAdd(&P.counters[0], c_nodes);
     atomicAdd(&P.counters[1], c_tests);
     atomicAdd(&P.counters[2], c_ins);

@@ -181,23 +181,39 @@ int launch_traverse_sparse(tknn_ctx* c, const trav::Params& P) {
   return TKNN_OK;
 }
 
-// warp-per-query variant for tiny rounds (the start-radius sample, a handful of stragglers, small query sets)
-int launch_traverse_warp(tknn_ctx* c, const trav::Params& P) {
-  const size_t smem = trav::warpq_smem(P.k);
-  const unsigned grid = (unsigned)((P.n_active + trav::WQ_WARPS - 1) / trav::WQ_WARPS);
+// warp-per-query (T = 32: tiny rounds, the start-radius sample, small query sets) or team-per-query (T = 4 / 8 / 16: sparse
+// rounds) variant
+template <int T>
+int launch_traverse_team(tknn_ctx* c, const trav::Params& P) {
+  const size_t smem = trav::warpq_smem(P.k, T);
+  const uint64_t per_block = (uint64_t)trav::WQ_WARPS * (32 / T);
+  const unsigned grid = (unsigned)((P.n_active + per_block - 1) / per_block);
   if (P.unresolved)  // the kernel ORs bits into the ballot words
     TK_CUDA(c, cudaMemsetAsync(P.unresolved, 0, sizeof(uint32_t) * (size_t)P.n_groups, c->stream));
   if (c->counters) {
-    auto kern = trav::traverse_warp_kernel<true>;
+    auto kern = trav::traverse_warp_kernel<true, T>;
     TK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, trav::WQ_WARPS * 32, smem, c->stream>>>(P);
   } else {
-    auto kern = trav::traverse_warp_kernel<false>;
+    auto kern = trav::traverse_warp_kernel<false, T>;
     TK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, trav::WQ_WARPS * 32, smem, c->stream>>>(P);
   }
   TK_CUDA(c, cudaGetLastError());
   return TKNN_OK;
+}
+
+int launch_traverse_warp(tknn_ctx* c, const trav::Params& P) { return launch_traverse_team<32>(c, P); }
+
+// sparse rounds: teams of c->sparse_team lanes per query, or (0) the thread-per-query kernel
+int launch_traverse_sparse_round(tknn_ctx* c, const trav::Params& P) {
+  const size_t team_smem = trav::warpq_smem(P.k, std::max(4, c->sparse_team));
+  if (c->sparse_team == 0 || team_smem > 200 * 1024) return launch_traverse_sparse(c, P);
+  switch (c->sparse_team) {
+    case 4: return launch_traverse_team<4>(c, P);
+    case 16: return launch_traverse_team<16>(c, P);
+    default: return launch_traverse_team<8>(c, P);
+  }
 }
 
 // One round = one traversal launch over the active queries; unresolved ones are compacted (order preserved) into the
@@ -297,7 +313,7 @@ int run_rounds(tknn_ctx* c, const Job& job, int* launches_io) {
     const bool tiny = c->warp_round_max > 0 &&
                       active <= (uint64_t)c->warp_round_max * (job.k > trav::LIST_MAX_K ? 4u : 1u);
     if (tiny) TK_TRY(launch_traverse_warp(c, P));
-    else if (sparse) TK_TRY(launch_traverse_sparse(c, P));
+    else if (sparse) TK_TRY(launch_traverse_sparse_round(c, P));
     else TK_TRY(launch_traverse<trav::MODE_KNN>(c, P));
     if (timed) TK_CUDA(c, cudaEventRecord(c->round_ev[4 * round + 3], c->stream));
     ++launches;
@@ -756,6 +772,10 @@ int tknn_set_option(tknn_ctx* c, int key, int64_t value) {
     case TKNN_OPT_SPECULATIVE_MAX:
       if (value < 0 || value > (int64_t)1 << 30) return fail(c, TKNN_EINVAL, "speculative maximum outside [0, 2^30]");
       c->speculative_max = (int)value;
+      return TKNN_OK;
+    case TKNN_OPT_SPARSE_TEAM:
+      if (value != 0 && value != 4 && value != 8 && value != 16) return fail(c, TKNN_EINVAL, "sparse team must be 0, 4, 8 or 16 lanes");
+      c->sparse_team = (int)value;
       return TKNN_OK;
     case TKNN_OPT_CURVE:
       if (value != 0 && value != 1 && !(value >= 101 && value <= 121))

@@ -573,3 +573,21 @@ def test_space_filling_curve_is_result_invariant(oracle, curve):
         assert_knn_equal(idx, dist, *ref, f"curve={curve}")
         qi, qd = t.query(x[:5000], 10, self_ids=np.arange(5000, dtype=np.int32))   # queries are coded on the same curve
         assert_knn_equal(qi, qd, ref[0][:5000], ref[1][:5000], f"query, curve={curve}")
+
+
+@pytest.mark.parametrize("team", [0, 4, 8, 16])
+@pytest.mark.parametrize("cloud,k", [("uniform", 10), ("lidar", 33), ("duplicates", 5)])
+def test_sparse_round_kernels_agree(oracle, team, cloud, k):
+    """Sparse rounds (more leftovers than the warp-per-query threshold, fewer than n / 8): one thread per query
+    (TKNN_OPT_SPARSE_TEAM = 0) or teams of 4 / 8 / 16 lanes per query give the same exact answer.  warp_round_max = 64
+    and a small start radius push most later rounds through the sparse kernel."""
+    from owlraytracing_b200 import TrueKNN
+
+    x = _kernel_choice_clouds()[cloud]
+    ref = oracle.knn_kdtree(x, k)
+    r_small = float(np.quantile(ref[1][:, -1], 0.96))                 # ~4 % of the queries miss in round 1
+    with TrueKNN(0, warp_round_max=64, speculative_max=0, sparse_team=team, counters=1) as t:
+        idx, dist = t.build(x).search(k, r_small)
+        st = t.stats()
+        assert_knn_equal(idx, dist, *ref, f"sparse_team={team} {cloud} k={k}")
+        assert st["rounds"] >= 2 and 64 < st["round_queries"][1] * 1 and st["round_queries"][1] * 8 <= x.shape[0]
