@@ -359,7 +359,7 @@ def run_gpu(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()  # nvidia-smi needs ~1 s to start streaming; it runs through warm-up and the timed region
-    t = TrueKNN(local_rank)
+    t = TrueKNN(local_rank, **{kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.opt})
     stream = torch.cuda.current_stream()
     t.set_stream(stream.cuda_stream)
     if world > 1:
@@ -663,6 +663,7 @@ def main():
     ap.add_argument("--output-chunks", type=int, default=0, help="e2e: Morton slices whose D2H overlaps the search (0 = library default)")
     ap.add_argument("--file-order-chunks", type=int, default=0, help="e2e through tknn_search: slices by original index (0 = default)")
     ap.add_argument("--e2e-shard-api", action="store_true", help="N=1 e2e through tknn_search_shard (compact Morton rows) instead of tknn_search")
+    ap.add_argument("--opt", action="append", default=[], help="library option for experiments, name=value (tknn_set_option)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-single", action="store_true", help="N > 1 strong scaling: skip the single-GPU run of the same workload")

@@ -21,7 +21,7 @@ constexpr int PASSES = 64 / RADIX_BITS;
 #define TKNN_SORT_ITEMS 16
 #endif
 constexpr int THREADS = TKNN_SORT_THREADS;
-static_assert(THREADS == RADIX, "onesweep_kernel: thread d owns digit d (status, histogram and scatter rows)");
+static_assert(THREADS >= RADIX && THREADS % 32 == 0, "onesweep_kernel: threads 0 .. RADIX-1 own the digits (status, histogram and scatter rows)");
 constexpr int WARPS = THREADS / 32;
 constexpr int ITEMS = TKNN_SORT_ITEMS;      // pairs per thread
 constexpr int TILE = THREADS * ITEMS;       // 4096 pairs per tile
@@ -147,63 +147,69 @@ static __global__ void __launch_bounds__(THREADS, TKNN_SORT_MINBLOCKS)
   }
   __syncthreads();
 
-  // thread d owns digit d: exclusive scan of the warp counters, publish the tile aggregate
+  // thread d < RADIX owns digit d (the first RADIX / 32 warps, all of them when THREADS == RADIX): exclusive scan of the
+  // warp counters, publish the tile aggregate
   const int d = threadIdx.x;
-  uint32_t total = 0;
-#pragma unroll
-  for (int w = 0; w < WARPS; ++w) {
-    const uint32_t c = s_warp_hist[w][d];
-    s_warp_hist[w][d] = total;
-    total += c;
-  }
+  const bool owner = d < RADIX;
+  uint32_t total = 0, inc = 0;
   uint32_t* st = status + (size_t)tile * RADIX;
-  atomicExch(&st[d], total | (tile == 0 ? FLAG_PREFIX : FLAG_AGG));
-
-  // exclusive scan of `total` over the 256 digits -> where each digit starts inside the tile
-  uint32_t inc = total;
+  if (owner) {
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(FULL_MASK, inc, o);
-    if (lane >= o) inc += t;
+    for (int w = 0; w < WARPS; ++w) {
+      const uint32_t c = s_warp_hist[w][d];
+      s_warp_hist[w][d] = total;
+      total += c;
+    }
+    atomicExch(&st[d], total | (tile == 0 ? FLAG_PREFIX : FLAG_AGG));
+
+    // exclusive scan of `total` over the 256 digits -> where each digit starts inside the tile
+    inc = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(FULL_MASK, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_wsum[warp] = inc;
   }
-  if (lane == 31) s_wsum[warp] = inc;
   __syncthreads();
-  uint32_t woff = 0;
-  for (int w = 0; w < warp; ++w) woff += s_wsum[w];
-  const uint32_t dstart = woff + inc - total;
-  s_digit_start[d] = dstart;
+  if (owner) {
+    uint32_t woff = 0;
+    for (int w = 0; w < warp; ++w) woff += s_wsum[w];
+    const uint32_t dstart = woff + inc - total;
+    s_digit_start[d] = dstart;
 
-  // decoupled look-back over the preceding tiles for digit d
-  // The walk is latency bound (one dependent global load per predecessor: 30 % of the pass's stall samples),
-  // so LOOKBACK predecessors are fetched at once and consumed in order; a predecessor that has published
-  // nothing yet restarts the window at that tile.
-  uint32_t excl = 0;
-  if (tile > 0) {
-    int64_t t = (int64_t)tile - 1;
-    bool done = false;
-    while (!done) {
-      uint32_t v[LOOKBACK];
-      // rows -1 .. -LOOKBACK in front of tile 0 hold "prefix 0" (scan_histogram_kernel), so the window needs
-      // no range test: the walk itself always ends at tile 0, which publishes FLAG_PREFIX directly
-      const volatile uint32_t* p = status + t * RADIX + d;
+    // decoupled look-back over the preceding tiles for digit d
+    // The walk is latency bound (one dependent global load per predecessor: 30 % of the pass's stall samples),
+    // so LOOKBACK predecessors are fetched at once and consumed in order; a predecessor that has published
+    // nothing yet restarts the window at that tile.
+    uint32_t excl = 0;
+    if (tile > 0) {
+      int64_t t = (int64_t)tile - 1;
+      bool done = false;
+      while (!done) {
+        uint32_t v[LOOKBACK];
+        // rows -1 .. -LOOKBACK in front of tile 0 hold "prefix 0" (scan_histogram_kernel), so the window needs
+        // no range test: the walk itself always ends at tile 0, which publishes FLAG_PREFIX directly
+        const volatile uint32_t* p = status + t * RADIX + d;
 #pragma unroll
-      for (int w = 0; w < LOOKBACK; ++w) v[w] = *(p - w * RADIX);
-      int used = 0;
+        for (int w = 0; w < LOOKBACK; ++w) v[w] = *(p - w * RADIX);
+        int used = 0;
 #pragma unroll
-      for (int w = 0; w < LOOKBACK; ++w) {
-        if (!done && used == w) {
-          if ((v[w] & FLAG_MASK) != 0) {
-            excl += v[w] & VALUE_MASK;
-            ++used;
-            if (v[w] & FLAG_PREFIX) done = true;
+        for (int w = 0; w < LOOKBACK; ++w) {
+          if (!done && used == w) {
+            if ((v[w] & FLAG_MASK) != 0) {
+              excl += v[w] & VALUE_MASK;
+              ++used;
+              if (v[w] & FLAG_PREFIX) done = true;
+            }
           }
         }
+        t -= used;  // used < LOOKBACK: tile t - used was not ready — poll again from there
       }
-      t -= used;  // used < LOOKBACK: tile t - used was not ready — poll again from there
+      atomicExch(&st[d], ((excl + total) & VALUE_MASK) | FLAG_PREFIX);
     }
-    atomicExch(&st[d], ((excl + total) & VALUE_MASK) | FLAG_PREFIX);
+    s_scatter[d] = bin_offset[d] + excl - dstart;  // global slot of tile-local position s is s_scatter[d] + s
   }
-  s_scatter[d] = bin_offset[d] + excl - dstart;  // global slot of tile-local position s is s_scatter[d] + s
   __syncthreads();
 
   // stage the tile in sorted order, then stream it out: runs of equal digits go to consecutive addresses

@@ -237,6 +237,34 @@ def test_stats_struct_layout_matches_header():
     assert off_round == _lib.Stats.round_ms.offset and off_h2d == _lib.Stats.h2d_bytes.offset
 
 
+def test_dist_stats_struct_layout_matches_header():
+    src = "#include <stdio.h>\n#include \"trueknn.h\"\nint main(){printf(\"%zu %zu %zu %zu\", sizeof(tknn_dist_stats), " \
+          "__builtin_offsetof(tknn_dist_stats, h2d_ms), __builtin_offsetof(tknn_dist_stats, search_total_ms), " \
+          "__builtin_offsetof(tknn_dist_stats, bytes_sent_search));return 0;}"
+    exe = "/tmp/tknn_dist_layout"
+    subprocess.run(["/usr/bin/gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src, text=True,
+                   check=True)
+    size, o1, o2, o3 = (int(v) for v in subprocess.run([exe], capture_output=True, text=True).stdout.split())
+    D = _lib.DistStats
+    assert size == ctypes.sizeof(D) and o1 == D.h2d_ms.offset and o2 == D.search_total_ms.offset and o3 == D.bytes_sent_search.offset
+
+
+def test_multi_gpu_calls_fail_cleanly_without_a_device():
+    """No GPU: tknn_create_multi reports an error code (no crash, no CPU fallback); comm calls on a null context are EINVAL."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    L = _lib.load()
+    ids = (ctypes.c_int * 2)(0, 1)
+    h = ctypes.c_void_p()
+    assert L.tknn_create_multi(ids, 2, _lib.SHARD_QUERIES, ctypes.byref(h)) != _lib.OK and not h.value
+    assert L.tknn_create_multi(ids, 0, _lib.SHARD_QUERIES, ctypes.byref(h)) == _lib.EINVAL
+    assert L.tknn_create_multi(ids, 2, 7, ctypes.byref(h)) == _lib.EINVAL
+    assert L.tknn_comm_init(None, 2, 0, ctypes.c_char_p(b"x" * 128)) == _lib.EINVAL
+    assert L.tknn_partition_owned(None) == 0
+
+
 def test_no_cpu_fallback_without_a_device():
     """Without a usable CUDA device tknn_create fails; nothing silently computes on the host."""
     import torch
@@ -346,3 +374,20 @@ def test_bench_cpu_arm_sampling_is_coherent_and_uses_all_cores(oracle):
     t.close()
     oracle.set_num_threads(os.cpu_count())
     assert oracle.num_threads() == os.cpu_count()
+
+
+def test_header_is_c99_and_links_from_plain_c(tmp_path):
+    """The boundary is a C ABI: include/trueknn.h must compile as C99 (-pedantic) and link from a plain C host — the shape
+    of the reference's own API test (tests/t00-c99-compliant-header/hostCode.c:30-46).  No CUDA call is made."""
+    src = tmp_path / "host.c"
+    src.write_text(
+        '#include "trueknn.h"\n#include <stdio.h>\n'
+        "int main(void) { tknn_stats s; tknn_dist_stats d; tknn_multi *m = 0; (void)s; (void)d; (void)m;\n"
+        '  printf("%d\\n", tknn_version()); return tknn_version() == TKNN_VERSION ? 0 : 1; }\n')
+    exe = tmp_path / "host"
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        str(src), "-L", lib_dir, "-ltrueknn", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "100"
