@@ -733,6 +733,12 @@ static __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
 // same strict pruning, same (d2, index) keys => same results.
 // ------------------------------------------------------------------------------------------------
 constexpr int SPARSE_THREADS = 128;
+// Measured (profiles/r2_ab_chunk.jsonl): 8 per step 0.414 vs 0.447 ms on cfg2's 97 478 leftovers but 1.98 vs 1.66 ms on cfg4's
+// 568 002; 16 and 32 per step 1.0 / 1.8 ms (registers, wasted tail loads).  4 stays.
+#ifndef TKNN_SPARSE_CHUNK
+#define TKNN_SPARSE_CHUNK 4
+#endif
+constexpr int SPARSE_CHUNK = TKNN_SPARSE_CHUNK;  // leaf points fetched per step of the thread-per-query kernel
 
 // + 3 slots of padding in front: list_insert prefetches up to three slots below the sentinel
 __host__ __device__ inline size_t sparse_smem(int k) { return ((size_t)(k + 1) * SPARSE_THREADS + 3 * 32) * sizeof(uint64_t); }
@@ -788,13 +794,13 @@ static __global__ void __launch_bounds__(SPARSE_THREADS) traverse_sparse_kernel(
         }
         const float4* lp = P.pts + (uint64_t)(uint32_t)(second ? ref1 : ref0);
         if (COUNT) c_tests += lcount;
-        // four independent loads in flight per step (the tail re-reads the last point; masked off)
-        for (int j = 0; j < lcount; j += 4) {
-          float4 p[4];
+        // SPARSE_CHUNK independent loads in flight per step (the tail re-reads the last point; masked off)
+        for (int j = 0; j < lcount; j += SPARSE_CHUNK) {
+          float4 p[SPARSE_CHUNK];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) p[u] = __ldg(lp + min(j + u, lcount - 1));
+          for (int u = 0; u < SPARSE_CHUNK; ++u) p[u] = __ldg(lp + min(j + u, lcount - 1));
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < SPARSE_CHUNK; ++u) {
             const float d = dist2(q.x, q.y, q.z, p[u].x, p[u].y, p[u].z);
             const int pid = __float_as_int(p[u].w);
             if (j + u < lcount && d <= bound && pid != self) {
