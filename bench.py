@@ -308,6 +308,12 @@ def roofline_block(t, wl, cfg, cs, nq, n_points, n_nodes, kern_ms_per_step, ms_p
 # GPU arm
 # --------------------------------------------------------------------------------------------------
 def run_gpu(args):
+    # ONE JSON line on stdout: whatever libraries print there (NCCL announces its version on stdout when a communicator
+    # is created) goes to stderr; the line itself is written to the saved descriptor at the end
+    json_fd = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -340,11 +346,6 @@ def run_gpu(args):
         if world > 1:
             dist.all_reduce(tm, op=dist.ReduceOp.SUM)
         return [int(v) for v in tm.tolist()]
-
-    # ONE JSON line on stdout: whatever libraries print there (NCCL announces its version on stdout) goes to stderr
-    json_fd = os.dup(1)
-    sys.stdout.flush()
-    os.dup2(2, 1)
 
     wl = resolve_workload(args)
     cfg = WORKLOADS[wl]
