@@ -123,3 +123,5 @@ int brute_core(tknn_ctx* c, const float4* d_qpts, uint64_t nq, int k, const uint
 
 // dist.cu: frees the multi-GPU state of a context (communicator included); called by tknn_destroy
 extern "C" void tknn_internal_free_dist(tknn_ctx* c);
+// dist.cu: a plain tknn_build invalidates the partitioned state of the context
+extern "C" void tknn_internal_dist_invalidate(tknn_ctx* c);

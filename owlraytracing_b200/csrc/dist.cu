@@ -1259,6 +1259,11 @@ int tknn_partition_verify(tknn_ctx* c, int k, int samples, const int32_t* gid, c
   return partition_verify(c, k, samples, gid, idx, dist, n_rows, n_checked, n_bad);
 }
 
+// called by tknn_build (trueknn.cu): a plain build replaces whatever a partitioned build left in the context
+void tknn_internal_dist_invalidate(tknn_ctx* c) {
+  if (c && c->dist) c->dist->partition_built = false;
+}
+
 // called by tknn_destroy (trueknn.cu)
 void tknn_internal_free_dist(tknn_ctx* c) {
   if (c && c->dist) { free_state(c->dist); c->dist = nullptr; }

@@ -808,6 +808,7 @@ int tknn_set_option(tknn_ctx* c, int key, int64_t value) {
 }
 
 int tknn_build(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int stride_floats) {
+  tknn_internal_dist_invalidate(c);
   return build_core(c, xyz, n, dim, stride_floats, false);
 }
 
