@@ -82,6 +82,11 @@ enum {
   ,TKNN_OPT_SPARSE_TEAM = 18    /* sparse rounds (more than WARP_ROUND_MAX leftover queries, fewer than n / SPARSE_DIVISOR): 0 (default)
                                   = one thread per query; 4, 8, 16 = a team of that many lanes shares one traversal (measured
                                   slower: cfg2's 97 478 leftovers 0.45 ms with threads, 0.78 / 0.65 / 0.63 ms with teams) */
+  ,TKNN_OPT_SORT_MODE = 19      /* build sort: 0 (default) = packed keys when they fit — (curve code << index bits | point index) in one
+                                  u64, as many code bits per axis as fit beside the index (at most 13: five 8-bit passes), sorted
+                                  keys-only at 16 B per point and pass; falls back to 1 when fewer than log2(n)/3 + 3 bits per axis
+                                  would fit (n > 2^28) or TKNN_OPT_MORTON_BITS asks for more than fit; 1 = (u64 code, u32 index)
+                                  pairs, log2(n)/3 + 8 bits per axis, 24 B per point and pass (round 1's sort) */
   ,TKNN_OPT_SPARSE_DIVISOR = 9 /* rounds >= 2 with fewer than n/divisor active queries run the
                                   thread-per-query kernel (default 8; 0 = never)                  */
 };
@@ -300,7 +305,7 @@ TKNN_API int tknn_multi_get_times(const tknn_multi* m, float* ms4);
 /* ---- introspection used by the tests and the bench (not part of the drop-in surface) ---- */
 
 /* Stand-alone onesweep radix sort of (u64 key, u32 value) pairs, stable, in place; device or host
- * pointers. */
+ * pointers.  values == NULL: keys only (the kernel variant behind the builder's packed keys). */
 TKNN_API int tknn_sort_pairs(tknn_ctx* ctx, uint64_t* keys, uint32_t* values, uint64_t n);
 
 /* Copies of the built BVH: nodes (n_nodes x 16 words), sorted points

@@ -50,7 +50,9 @@ struct tknn_ctx {
   int speculative_max = 1 << 20;  // searches of at most this many queries launch round 2 without a host decision (0 = never)
   int approx_filter = 0;
   int tie_pruning = 0;        // 0 = auto (on when the build saw leaves of coincident points), 1 = on, 2 = off
-  int morton_bits = 0;        // 0 = auto (ceil(log2 n / 3) + 8, clamped to [10, 21])
+  int morton_bits = 0;        // 0 = auto (packed sort: as many as fit beside the index, <= 13; pair sort: ceil(log2 n / 3) + 8 in [10, 21])
+  int sort_mode = 0;          // 0 = packed (code, index) keys when they fit, 1 = (code, index) pairs (TKNN_OPT_SORT_MODE)
+  int built_idx_bits = 0;     // index bits of the packed keys of the current BVH (0: pair sort)
   bool has_dup_leaves = false; // the build found a leaf of coincident points => tie-pruning kernel variant
   int built_morton_bits = 21; // what the current BVH was built with (queries are coded the same way)
   int curve = 1;              // space-filling curve of the next build: 1 = Hilbert (default), 0 = Morton

@@ -766,7 +766,7 @@ static int partition_build(tknn_ctx* c, const float* xyz_local, uint64_t n_local
   uint32_t* vals = c->b_vals_a.as<uint32_t>();
   TK_CUDA(c, cudaMemsetAsync(S->hist.p, 0, N_CELLS * sizeof(uint32_t), st));
   if (n_local) {
-    lbvh::morton_kernel<<<blocks_for(n_local, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, n_local, dim, stride, ob, 21, 0, keys, vals);
+    lbvh::morton_kernel<<<blocks_for(n_local, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, n_local, dim, stride, ob, 21, 0, 0, keys, vals);
     cell_hist_kernel<<<blocks_for(n_local, 256), 256, 0, st>>>(keys, n_local, S->hist.as<uint32_t>());
     TK_CUDA(c, cudaGetLastError());
   }

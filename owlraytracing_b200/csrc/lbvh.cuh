@@ -111,7 +111,8 @@ __device__ __forceinline__ void hilbert_transpose(uint32_t& x0, uint32_t& x1, ui
 // at 10 M points: 0.22 -> 0.15 ms).
 static __global__ void __launch_bounds__(THREADS) morton_kernel(const float* __restrict__ xyz, uint64_t n, int dim, int stride,
                                                          const uint32_t* __restrict__ bounds, int bits, int curve,
-                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                                         int idx_bits, uint64_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ vals) {
   const uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
   if (i >= n) return;
   const float lx = ordered_to_float(bounds[0]), ly = ordered_to_float(bounds[1]), lz = ordered_to_float(bounds[2]);
@@ -134,20 +135,29 @@ static __global__ void __launch_bounds__(THREADS) morton_kernel(const float* __r
     cy = (hy << low) | (cy & lm);
     cz = (hz << low) | (cz & lm);
   }
-  keys[i] = (spread21(cx) << 2) | (spread21(cy) << 1) | spread21(cz);
-  vals[i] = (uint32_t)i;
+  const uint64_t code = (spread21(cx) << 2) | (spread21(cy) << 1) | spread21(cz);
+  if (idx_bits > 0) {
+    // packed key: the code above the point's index (3 * bits + idx_bits <= 64).  The sort runs on the code bits only
+    // and moves 8 instead of 12 bytes per point and pass; keys are distinct, ties of the code are in index order.
+    keys[i] = (code << idx_bits) | i;
+  } else {
+    keys[i] = code;
+    vals[i] = (uint32_t)i;
+  }
 }
 
 // sorted float4 points: (x, y, z, id bits).  The id is the row number of the point in the caller's array, or —
 // ids_in_w (point-partitioned driver) — the bits of the row's 4th float, so that a rank's BVH carries GLOBAL ids
 // and its (d2, id) tie-breaks are the global ones.  bad_flag (optional): set when a coordinate is not finite.
+// The source row of sorted position i is order[i], or — order == nullptr — the low idx_bits bits of packed[i].
 static __global__ void __launch_bounds__(THREADS) gather_points_kernel(const float* __restrict__ xyz, int dim, int stride,
-                                                                const uint32_t* __restrict__ order, uint64_t n,
+                                                                const uint32_t* __restrict__ order,
+                                                                const uint64_t* __restrict__ packed, int idx_bits, uint64_t n,
                                                                 int ids_in_w, float4* __restrict__ pts,
                                                                 uint32_t* __restrict__ bad_flag = nullptr) {
   const uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
   if (i >= n) return;
-  const uint32_t src = order[i];
+  const uint32_t src = order ? order[i] : (uint32_t)(packed[i] & ((1ull << idx_bits) - 1ull));
   const float* p = xyz + (uint64_t)src * (uint64_t)stride;
   const float x = p[0], y = p[1], z = dim > 2 ? p[2] : 0.0f;
   if (bad_flag && !(isfinite(x) && isfinite(y) && isfinite(z))) *bad_flag = 1u;

@@ -29,24 +29,30 @@ constexpr uint32_t FLAG_AGG = 1u << 30;     // tile aggregate published
 constexpr uint32_t FLAG_PREFIX = 2u << 30;  // inclusive prefix published
 constexpr uint32_t FLAG_MASK = 3u << 30;
 constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
-constexpr int LOOKBACK = 8;                   // predecessors fetched per look-back step
+#ifndef TKNN_SORT_LOOKBACK
+#define TKNN_SORT_LOOKBACK 4
+#endif
+constexpr int LOOKBACK = TKNN_SORT_LOOKBACK;  // predecessors fetched per look-back step
 constexpr uint64_t MAX_N = (1ull << 30) - 1;  // counts share a word with the two flag bits
 
 constexpr size_t DYN_SMEM = (size_t)TILE * (sizeof(uint64_t) + sizeof(uint32_t));
+constexpr size_t DYN_SMEM_KEYS = (size_t)TILE * sizeof(uint64_t);
 
 __host__ __device__ inline uint32_t num_tiles(uint64_t n) { return (uint32_t)((n + TILE - 1) / TILE); }
 
 // hist[pass][digit] += count, all passes in one read of the keys.
+// Digit p is bits [shift0 + 8p, shift0 + 8p + 8) of the key (shift0 > 0: packed (code, index) keys, sort_keys below).
 static __global__ void __launch_bounds__(THREADS) histogram_kernel(const uint64_t* __restrict__ keys, uint64_t n,
-                                                            uint32_t* __restrict__ hist) {
+                                                            uint32_t* __restrict__ hist, int shift0, int passes) {
   __shared__ uint32_t s_hist[PASSES * RADIX];
   for (int i = threadIdx.x; i < PASSES * RADIX; i += THREADS) s_hist[i] = 0;
   __syncthreads();
   const uint64_t stride = (uint64_t)gridDim.x * THREADS;
   for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride) {
-    const uint64_t key = keys[i];
+    const uint64_t key = keys[i] >> shift0;
 #pragma unroll
-    for (int p = 0; p < PASSES; ++p) atomicAdd(&s_hist[p * RADIX + (uint32_t)((key >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+    for (int p = 0; p < PASSES; ++p)
+      if (p < passes) atomicAdd(&s_hist[p * RADIX + (uint32_t)((key >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < PASSES * RADIX; i += THREADS) {
@@ -92,24 +98,44 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d) {
   return peers;
 }
 
-// One onesweep pass over digit `shift / 8`.
+// One onesweep pass over the 8-bit digit at bit `shift`.
+// PAIRS = true: (u64 key, u32 value) pairs, 24 B moved per pair.  PAIRS = false: keys only (sort_keys: the builder packs
+// (curve code, point index) into one u64, the index in the low bits that no pass touches), 16 B moved per key, no value
+// registers, a 32 KB instead of a 48 KB tile, 4 instead of 3 resident blocks.
+//
+// The inter-tile dependency of a single-sweep sort is the look-back: a tile cannot place a key before every preceding tile
+// has published its digit counts.  Round 1's kernel published a tile's aggregate only after it had RANKED its keys (half of
+// its life) and its inclusive prefix after its own look-back, so tiles waited on work that has nothing to do with the
+// counts.  Here the per-warp digit counts are taken first, with shared-memory atomics (order-free: only the totals matter),
+// the aggregate is published right behind the load, and the look-back runs BEFORE the ranking: the chain between consecutive
+// tiles shrinks to load + count + one window, and everything expensive (ranking, staging, streaming out) is independent
+// per tile.  Because the counters then already hold each (warp, digit) run's first slot in the sorted tile, the ranking
+// loop writes every key straight to its slot: no rank registers, no second pass over the keys.
+// Measured, sort of 10 M / 100 M packed keys, 5 passes (profiles/r2_ab_sortkeys*.jsonl): round 1's order of phases 0.468 / 3.36 ms,
+// this kernel 0.441 / 3.66 ms with windows of 8 predecessors, 0.427 / 3.48 ms with windows of 4 (kept), 0.431 / 3.42 with 2,
+// 0.466 / 3.73 with 1, 0.476 / 4.02 with 16, 0.554 / 4.84 with 32: the window loads are L2 traffic of the size of the keys
+// themselves (a window of 8 rows is 8 KB per tile against a 32 KB tile), so wider windows lose more than they hide.
+// 5 resident blocks (51 registers), tiles of 3072 or 2048 keys: slower (0.45, 0.48, 0.57 ms).
 #ifndef TKNN_SORT_MINBLOCKS
 #define TKNN_SORT_MINBLOCKS 3
 #endif
-static __global__ void __launch_bounds__(THREADS, TKNN_SORT_MINBLOCKS)
+#ifndef TKNN_SORT_MINBLOCKS_KEYS
+#define TKNN_SORT_MINBLOCKS_KEYS 4
+#endif
+template <bool PAIRS>
+static __global__ void __launch_bounds__(THREADS, PAIRS ? TKNN_SORT_MINBLOCKS : TKNN_SORT_MINBLOCKS_KEYS)
     onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                    uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint64_t n, int shift,
-                    const uint32_t* __restrict__ bin_offset, uint32_t* status, uint32_t* tile_counter) {
+                          uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint64_t n, int shift,
+                          const uint32_t* __restrict__ bin_offset, uint32_t* status, uint32_t* tile_counter) {
+  static_assert(THREADS == RADIX, "onesweep_kernel: one digit owner per thread");
   __shared__ uint32_t s_warp_hist[WARPS][RADIX];
-  __shared__ uint32_t s_digit_start[RADIX];
   __shared__ uint32_t s_scatter[RADIX];
   __shared__ uint32_t s_wsum[WARPS];
   __shared__ uint32_t s_tile;
   extern __shared__ __align__(16) unsigned char s_dyn[];
   uint64_t* s_keys = reinterpret_cast<uint64_t*>(s_dyn);
-  uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + TILE);
+  uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + TILE);  // PAIRS only
 
-  // dynamic tile ids: a tile only ever waits on tiles that started before it (deadlock freedom)
   if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
   for (int i = threadIdx.x; i < WARPS * RADIX; i += THREADS) (&s_warp_hist[0][0])[i] = 0;
   __syncthreads();
@@ -119,80 +145,69 @@ static __global__ void __launch_bounds__(THREADS, TKNN_SORT_MINBLOCKS)
   const uint32_t lt_mask = (1u << lane) - 1u;
 
   uint64_t key[ITEMS];
-  uint32_t val[ITEMS];
-  uint32_t rank[ITEMS];
+  uint32_t val[PAIRS ? ITEMS : 1];
   const uint64_t wbase = base + (uint64_t)warp * (32 * ITEMS);
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     const uint64_t idx = wbase + i * 32 + lane;
     const bool ok = idx < n;
     key[i] = ok ? keys_in[idx] : ~0ull;  // padding ranks after every real key of digit 255
-    val[i] = ok ? vals_in[idx] : 0u;
+    if (PAIRS) val[i] = ok ? vals_in[idx] : 0u;
   }
-  // warp-local stable ranking: lanes holding the same digit find each other (match_digit); the
-  // lowest of them bumps the warp's digit counter for the whole peer group.
+  // early counts
 #pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const uint32_t d = (uint32_t)(key[i] >> shift) & (RADIX - 1);
-    const uint32_t peers = match_digit(d);
-    const int leader = __ffs(peers) - 1;
-    uint32_t old = 0;
-    if (lane == leader) {
-      old = s_warp_hist[warp][d];
-      s_warp_hist[warp][d] = old + __popc(peers);
-    }
-    old = __shfl_sync(FULL_MASK, old, leader);
-    rank[i] = old + __popc(peers & lt_mask);
-    __syncwarp();
-  }
+  for (int i = 0; i < ITEMS; ++i) atomicAdd(&s_warp_hist[warp][(uint32_t)(key[i] >> shift) & (RADIX - 1)], 1u);
   __syncthreads();
 
-  // thread d < RADIX owns digit d (the first RADIX / 32 warps, all of them when THREADS == RADIX): exclusive scan of the
-  // warp counters, publish the tile aggregate
+  // thread d owns digit d: tile total -> aggregate, published at once
   const int d = threadIdx.x;
-  const bool owner = d < RADIX;
-  uint32_t total = 0, inc = 0;
+  uint32_t total = 0;
+#pragma unroll
+  for (int w = 0; w < WARPS; ++w) total += s_warp_hist[w][d];
   uint32_t* st = status + (size_t)tile * RADIX;
-  if (owner) {
+  atomicExch(&st[d], total | (tile == 0 ? FLAG_PREFIX : FLAG_AGG));
+  // first look-back window in flight while the tile-local scan runs
+  uint32_t v[LOOKBACK];
+  int64_t lt = (int64_t)tile - 1;
+  {
+    const volatile uint32_t* p = status + lt * RADIX + d;  // tile 0 reads the "prefix 0" rows in front of the array
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) {
-      const uint32_t c = s_warp_hist[w][d];
-      s_warp_hist[w][d] = total;
-      total += c;
-    }
-    atomicExch(&st[d], total | (tile == 0 ? FLAG_PREFIX : FLAG_AGG));
-
-    // exclusive scan of `total` over the 256 digits -> where each digit starts inside the tile
-    inc = total;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(FULL_MASK, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_wsum[warp] = inc;
+    for (int w = 0; w < LOOKBACK; ++w) v[w] = *(p - w * RADIX);
   }
+  uint32_t inc = total;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(FULL_MASK, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_wsum[warp] = inc;
   __syncthreads();
-  if (owner) {
+  uint32_t dstart;
+  {
     uint32_t woff = 0;
     for (int w = 0; w < warp; ++w) woff += s_wsum[w];
-    const uint32_t dstart = woff + inc - total;
-    s_digit_start[d] = dstart;
-
-    // decoupled look-back over the preceding tiles for digit d
-    // The walk is latency bound (one dependent global load per predecessor: 30 % of the pass's stall samples),
-    // so LOOKBACK predecessors are fetched at once and consumed in order; a predecessor that has published
-    // nothing yet restarts the window at that tile.
+    dstart = woff + inc - total;  // where digit d starts inside the sorted tile
+    uint32_t run = dstart;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {  // counter (w, d) := first slot of warp w's run of digit d
+      const uint32_t c = s_warp_hist[w][d];
+      s_warp_hist[w][d] = run;
+      run += c;
+    }
+  }
+  // decoupled look-back (LOOKBACK predecessors per step, consumed in order; a predecessor that has published nothing yet
+  // restarts the window at that tile)
+  {
     uint32_t excl = 0;
     if (tile > 0) {
-      int64_t t = (int64_t)tile - 1;
-      bool done = false;
+      bool done = false, loaded = true;
       while (!done) {
-        uint32_t v[LOOKBACK];
-        // rows -1 .. -LOOKBACK in front of tile 0 hold "prefix 0" (scan_histogram_kernel), so the window needs
-        // no range test: the walk itself always ends at tile 0, which publishes FLAG_PREFIX directly
-        const volatile uint32_t* p = status + t * RADIX + d;
+        if (!loaded) {
+          const volatile uint32_t* p = status + lt * RADIX + d;
 #pragma unroll
-        for (int w = 0; w < LOOKBACK; ++w) v[w] = *(p - w * RADIX);
+          for (int w = 0; w < LOOKBACK; ++w) v[w] = *(p - w * RADIX);
+        }
+        loaded = false;
         int used = 0;
 #pragma unroll
         for (int w = 0; w < LOOKBACK; ++w) {
@@ -204,7 +219,7 @@ static __global__ void __launch_bounds__(THREADS, TKNN_SORT_MINBLOCKS)
             }
           }
         }
-        t -= used;  // used < LOOKBACK: tile t - used was not ready — poll again from there
+        lt -= used;
       }
       atomicExch(&st[d], ((excl + total) & VALUE_MASK) | FLAG_PREFIX);
     }
@@ -212,22 +227,34 @@ static __global__ void __launch_bounds__(THREADS, TKNN_SORT_MINBLOCKS)
   }
   __syncthreads();
 
-  // stage the tile in sorted order, then stream it out: runs of equal digits go to consecutive addresses
+  // warp-local stable ranking straight into the sorted tile: lanes holding the same digit find each other (match_digit);
+  // the lowest of them advances the (warp, digit) counter for the whole peer group
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     const uint32_t dg = (uint32_t)(key[i] >> shift) & (RADIX - 1);
-    const uint32_t pos = s_digit_start[dg] + s_warp_hist[warp][dg] + rank[i];
+    const uint32_t peers = match_digit(dg);
+    const int leader = __ffs(peers) - 1;
+    uint32_t old = 0;
+    if (lane == leader) {
+      old = s_warp_hist[warp][dg];
+      s_warp_hist[warp][dg] = old + __popc(peers);
+    }
+    old = __shfl_sync(FULL_MASK, old, leader);
+    const uint32_t pos = old + __popc(peers & lt_mask);
     s_keys[pos] = key[i];
-    s_vals[pos] = val[i];
+    if (PAIRS) s_vals[pos] = val[i];
+    __syncwarp();
   }
   __syncthreads();
+
+  // stream the tile out: runs of equal digits go to consecutive addresses
   const uint32_t tile_n = (uint32_t)((n - base) < (uint64_t)TILE ? (n - base) : (uint64_t)TILE);
   for (uint32_t s = threadIdx.x; s < tile_n; s += THREADS) {
     const uint64_t k = s_keys[s];
     const uint32_t dg = (uint32_t)(k >> shift) & (RADIX - 1);
     const uint32_t dst = s_scatter[dg] + s;
     keys_out[dst] = k;
-    vals_out[dst] = s_vals[s];
+    if (PAIRS) vals_out[dst] = s_vals[s];
   }
 }
 
@@ -235,40 +262,63 @@ static __global__ void __launch_bounds__(THREADS, TKNN_SORT_MINBLOCKS)
 // status[tiles*RADIX]
 inline size_t temp_words(uint64_t n) { return (size_t)PASSES * RADIX + 16 + (size_t)(LOOKBACK + num_tiles(n)) * RADIX; }
 
-// Sorts (keys_a, vals_a) on the low 8 * passes key bits (keys must be zero above them) using
-// (keys_b, vals_b) as the alternate buffer.  The result ends in the `a` buffers when `passes` is even
-// and in the `b` buffers when it is odd (*in_b tells which).  Returns the number of kernels launched.
-inline int sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint64_t n,
-                      uint32_t* temp, int sm_count, cudaStream_t stream, int passes = PASSES, bool* in_b = nullptr) {
+// Sorts (keys_a, vals_a) on the key bits [shift0, shift0 + 8 * passes) (stable; keys must agree above them) using
+// (keys_b, vals_b) as the alternate buffer.  vals_a == nullptr: keys only (PAIRS = false).  The result ends in the `a`
+// buffers when `passes` is even and in the `b` buffers when it is odd (*in_b tells which).  Returns the number of
+// kernels launched.
+inline int sort_impl(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint64_t n, uint32_t* temp,
+                     int sm_count, cudaStream_t stream, int shift0, int passes, bool* in_b) {
   if (in_b) *in_b = false;
   if (n == 0) return 0;
   if (passes < 1) passes = 1;
   if (passes > PASSES) passes = PASSES;
+  if (shift0 < 0) shift0 = 0;
+  if (shift0 + RADIX_BITS * (passes - 1) > 63) passes = (63 - shift0) / RADIX_BITS + 1;
+  const bool pairs = vals_a != nullptr;
   uint32_t* hist = temp;
   uint32_t* counters = temp + PASSES * RADIX;
   uint32_t* status_pad = counters + 16;
   uint32_t* status = status_pad + LOOKBACK * RADIX;
   const uint32_t tiles = num_tiles(n);
   cudaMemsetAsync(temp, 0, sizeof(uint32_t) * (PASSES * RADIX + 16), stream);
-  cudaFuncSetAttribute(onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM);
+  const size_t dyn = pairs ? DYN_SMEM : DYN_SMEM_KEYS;
+  if (pairs) cudaFuncSetAttribute(onesweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  else cudaFuncSetAttribute(onesweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   uint64_t hb = (n + THREADS * 8 - 1) / (THREADS * 8);
   const uint64_t hmax = (uint64_t)sm_count * 8;
   if (hb > hmax) hb = hmax;
-  histogram_kernel<<<(unsigned)hb, THREADS, 0, stream>>>(keys_a, n, hist);
+  histogram_kernel<<<(unsigned)hb, THREADS, 0, stream>>>(keys_a, n, hist, shift0, passes);
   scan_histogram_kernel<<<PASSES, RADIX, 0, stream>>>(hist, status_pad);
   int launches = 2;
   uint64_t *kin = keys_a, *kout = keys_b;
   uint32_t *vin = vals_a, *vout = vals_b;
   for (int p = 0; p < passes; ++p) {
     cudaMemsetAsync(status, 0, sizeof(uint32_t) * (size_t)tiles * RADIX, stream);
-    onesweep_kernel<<<tiles, THREADS, DYN_SMEM, stream>>>(kin, vin, kout, vout, n, p * RADIX_BITS, hist + p * RADIX,
-                                                          status, counters + p);
+    if (pairs)
+      onesweep_kernel<true><<<tiles, THREADS, dyn, stream>>>(kin, vin, kout, vout, n, shift0 + p * RADIX_BITS, hist + p * RADIX,
+                                                            status, counters + p);
+    else
+      onesweep_kernel<false><<<tiles, THREADS, dyn, stream>>>(kin, nullptr, kout, nullptr, n, shift0 + p * RADIX_BITS,
+                                                             hist + p * RADIX, status, counters + p);
     ++launches;
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
   }
   if (in_b) *in_b = (passes & 1) != 0;
   return launches;
+}
+
+inline int sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint64_t n,
+                      uint32_t* temp, int sm_count, cudaStream_t stream, int passes = PASSES, bool* in_b = nullptr) {
+  return sort_impl(keys_a, vals_a, keys_b, vals_b, n, temp, sm_count, stream, 0, passes, in_b);
+}
+
+// Keys only, digits from bit shift0 up: the builder's packed (curve code << index bits | point index) keys — the low
+// `shift0` bits (the index) ride along untouched, and because the input is in index order the result equals the stable
+// pair sort of (code, index).
+inline int sort_keys(uint64_t* keys_a, uint64_t* keys_b, uint64_t n, uint32_t* temp, int sm_count, cudaStream_t stream,
+                     int shift0, int passes, bool* in_b = nullptr) {
+  return sort_impl(keys_a, nullptr, keys_b, nullptr, n, temp, sm_count, stream, shift0, passes, in_b);
 }
 
 }  // namespace rsort

@@ -438,6 +438,33 @@ int auto_morton_bits(uint64_t n) {
   return std::min(21, std::max(10, (lg + 2) / 3 + 8));
 }
 
+// Key layout of a build (TKNN_OPT_SORT_MODE, TKNN_OPT_MORTON_BITS).  Packed: the curve code sits above the point's index
+// in one u64 and the sort moves keys only.  The code gets as many bits per axis as fit beside the index, at most 13
+// (39 bits: five 8-bit passes) — 13 bits at 10 M points are cells 32x finer per axis than the mean point spacing, 12 bits
+// at 100 M points 9x — and one bit per axis less where that saves a whole pass and still leaves log2(n)/3 + 4.  Points
+// that share a cell are ordered by index: tree quality at the scale of one cell, never exactness.
+// *idx_bits == 0: pair sort.
+void choose_key_layout(const tknn_ctx* c, uint64_t n, int* mbits, int* idx_bits) {
+  int lg = 0;
+  while (((uint64_t)1 << lg) < n) ++lg;
+  const int ib = std::max(1, lg), spacing = (lg + 2) / 3, fit = (64 - ib) / 3;
+  *idx_bits = 0;
+  if (c->morton_bits > 0) {
+    *mbits = c->morton_bits;
+    if (c->sort_mode == 0 && 3 * c->morton_bits + ib <= 64) *idx_bits = ib;
+    return;
+  }
+  if (c->sort_mode == 0 && fit >= spacing + 3) {
+    int b = std::min(13, fit);
+    const int spare = 3 * b - 8 * ((3 * b - 1) / 8);  // code bits in the last, partial pass
+    if (spare <= 3 && b - 1 >= spacing + 4) --b;
+    *mbits = b;
+    *idx_bits = ib;
+    return;
+  }
+  *mbits = auto_morton_bits(n);
+}
+
 // Hilbert levels of the key kernel (lbvh.cuh: morton_kernel): two levels below the one where a cell holds one point
 int hilbert_levels(uint64_t n, int bits, int forced = 0) {
   if (forced > 0) return std::max(2, std::min(bits, forced));
@@ -773,6 +800,10 @@ int tknn_set_option(tknn_ctx* c, int key, int64_t value) {
       if (value < 0 || value > (int64_t)1 << 30) return fail(c, TKNN_EINVAL, "speculative maximum outside [0, 2^30]");
       c->speculative_max = (int)value;
       return TKNN_OK;
+    case TKNN_OPT_SORT_MODE:
+      if (value != 0 && value != 1) return fail(c, TKNN_EINVAL, "sort mode must be 0 (packed keys when they fit) or 1 (pairs)");
+      c->sort_mode = (int)value;
+      return TKNN_OK;
     case TKNN_OPT_SPARSE_TEAM:
       if (value != 0 && value != 4 && value != 8 && value != 16) return fail(c, TKNN_EINVAL, "sparse team must be 0, 4, 8 or 16 lanes");
       c->sparse_team = (int)value;
@@ -888,20 +919,25 @@ int tknn::host::build_core(tknn_ctx* c, const float* xyz, uint64_t n, int dim, i
   TK_B(ensure(c, keys_b, n * sizeof(uint64_t)));
   TK_B(ensure(c, vals_a, n * sizeof(uint32_t)));
   TK_B(ensure(c, vals_b, n * sizeof(uint32_t)));
-  const int mbits = c->morton_bits > 0 ? c->morton_bits : auto_morton_bits(n);
+  int mbits = 0, idx_bits = 0;
+  choose_key_layout(c, n, &mbits, &idx_bits);
   lbvh::morton_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, n, dim, stride_floats, sc + SC_BOUNDS, mbits,
-                                                                             c->curve ? hilbert_levels(n, mbits, c->curve_levels) : 0, keys_a.as<uint64_t>(),
-                                                                             vals_a.as<uint32_t>());
+                                                                             c->curve ? hilbert_levels(n, mbits, c->curve_levels) : 0, idx_bits,
+                                                                             keys_a.as<uint64_t>(), vals_a.as<uint32_t>());
   ++launches;
   TK_BC(cudaEventRecord(c->ev[3], st));
 
   // ---- onesweep radix sort ----
   TK_B(ensure(c, sort_tmp, rsort::temp_words(n) * sizeof(uint32_t)));
   bool sorted_in_b = false;
-  launches += rsort::sort_pairs(keys_a.as<uint64_t>(), vals_a.as<uint32_t>(), keys_b.as<uint64_t>(), vals_b.as<uint32_t>(), n,
-                                sort_tmp.as<uint32_t>(), c->sm_count, st, (3 * mbits + 7) / 8, &sorted_in_b);
+  if (idx_bits > 0)
+    launches += rsort::sort_keys(keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), n, sort_tmp.as<uint32_t>(), c->sm_count, st, idx_bits,
+                                 (3 * mbits + 7) / 8, &sorted_in_b);
+  else
+    launches += rsort::sort_pairs(keys_a.as<uint64_t>(), vals_a.as<uint32_t>(), keys_b.as<uint64_t>(), vals_b.as<uint32_t>(), n,
+                                  sort_tmp.as<uint32_t>(), c->sm_count, st, (3 * mbits + 7) / 8, &sorted_in_b);
   const uint64_t* skeys = sorted_in_b ? keys_b.as<uint64_t>() : keys_a.as<uint64_t>();
-  const uint32_t* svals = sorted_in_b ? vals_b.as<uint32_t>() : vals_a.as<uint32_t>();
+  const uint32_t* svals = idx_bits > 0 ? nullptr : (sorted_in_b ? vals_b.as<uint32_t>() : vals_a.as<uint32_t>());
   TK_BC(cudaGetLastError());
   TK_BC(cudaEventRecord(c->ev[4], st));
 
@@ -927,8 +963,8 @@ int tknn::host::build_core(tknn_ctx* c, const float* xyz, uint64_t n, int dim, i
   lbvh::leaf_emit_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(
       ballots.as<uint32_t>(), c->offsets.as<uint32_t>(), skeys, n, m, c->leaf_start.as<uint32_t>(),
       leaf_key.as<uint64_t>());
-  lbvh::gather_points_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, dim, stride_floats,
-                                                                                   svals, n, ids_in_w ? 1 : 0, c->pts.as<float4>());
+  lbvh::gather_points_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, dim, stride_floats, svals, skeys, idx_bits,
+                                                                                   n, ids_in_w ? 1 : 0, c->pts.as<float4>());
   launches += 2;
   TK_BC(cudaEventRecord(c->ev[5], st));
 
@@ -975,6 +1011,7 @@ int tknn::host::build_core(tknn_ctx* c, const float* xyz, uint64_t n, int dim, i
   S.n_leaves = m;
   S.n_nodes = m - 1;
   c->built_morton_bits = mbits;
+  c->built_idx_bits = idx_bits;
   c->built_curve = c->curve ? hilbert_levels(n, mbits, c->curve_levels) : 0;
   c->has_dup_leaves = dupleaf != 0;
   S.build_launches = (uint32_t)launches;
@@ -1096,14 +1133,14 @@ int tknn_query(tknn_ctx* c, const float* queries, uint64_t nq, int dim, int stri
   TK_BC(cudaMemsetAsync(sc + SC_ERROR, 0, 2 * sizeof(uint32_t), st));
   const int qbits = c->built_morton_bits;
   lbvh::morton_kernel<<<blocks_for(nq, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_q, nq, dim, stride_floats, sc + SC_BOUNDS, qbits,
-                                                                              c->built_curve, keys_a.as<uint64_t>(), vals_a.as<uint32_t>());
+                                                                              c->built_curve, 0, keys_a.as<uint64_t>(), vals_a.as<uint32_t>());
   ++launches;
   bool q_in_b = false;
   launches += rsort::sort_pairs(keys_a.as<uint64_t>(), vals_a.as<uint32_t>(), keys_b.as<uint64_t>(), vals_b.as<uint32_t>(), nq,
                                 sort_tmp.as<uint32_t>(), c->sm_count, st, (3 * qbits + 7) / 8, &q_in_b);
   const uint32_t* qorder = q_in_b ? vals_b.as<uint32_t>() : vals_a.as<uint32_t>();
   lbvh::gather_points_kernel<<<blocks_for(nq, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_q, dim, stride_floats,
-                                                                                    qorder, nq, 0, qpts.as<float4>(), sc + SC_QBAD);
+                                                                                    qorder, nullptr, 0, nq, 0, qpts.as<float4>(), sc + SC_QBAD);
   TK_BC(cudaGetLastError());
   ++launches;
   const int32_t* d_sid_sorted = nullptr;
@@ -1335,11 +1372,11 @@ int tknn_get_stats(const tknn_ctx* c, tknn_stats* out) {
 int tknn_sort_pairs(tknn_ctx* c, uint64_t* keys, uint32_t* values, uint64_t n) {
   TK_TRY(check_ctx(c));
   if (n == 0) return TKNN_OK;
-  if (!keys || !values) return fail(c, TKNN_EINVAL, "null array");
+  if (!keys) return fail(c, TKNN_EINVAL, "null array");
   if (n > rsort::MAX_N) return fail(c, TKNN_EINVAL, "n too large");
   ScopedDevice sd(c->device);
   cudaStream_t st = c->stream;
-  const bool kd = is_device_ptr(keys), vd = is_device_ptr(values);
+  const bool kd = is_device_ptr(keys), vd = !values || is_device_ptr(values);  // values == nullptr: keys only
   DevBuf ka, kb, va, vb, tmp;
   auto cleanup = [&]() { for (DevBuf* b : {&ka, &kb, &va, &vb, &tmp}) release(*b); };
 #define TK_B(expr) do { int rc_ = (expr); if (rc_ != TKNN_OK) { cleanup(); return rc_; } } while (0)
@@ -1350,9 +1387,10 @@ int tknn_sort_pairs(tknn_ctx* c, uint64_t* keys, uint32_t* values, uint64_t n) {
   if (!kd) { TK_B(ensure(c, ka, n * sizeof(uint64_t))); dk = ka.as<uint64_t>(); TK_BC(cudaMemcpyAsync(dk, keys, n * 8, cudaMemcpyHostToDevice, st)); }
   if (!vd) { TK_B(ensure(c, va, n * sizeof(uint32_t))); dv = va.as<uint32_t>(); TK_BC(cudaMemcpyAsync(dv, values, n * 4, cudaMemcpyHostToDevice, st)); }
   TK_B(ensure(c, kb, n * sizeof(uint64_t)));
-  TK_B(ensure(c, vb, n * sizeof(uint32_t)));
+  if (values) TK_B(ensure(c, vb, n * sizeof(uint32_t)));
   TK_B(ensure(c, tmp, rsort::temp_words(n) * sizeof(uint32_t)));
-  rsort::sort_pairs(dk, dv, kb.as<uint64_t>(), vb.as<uint32_t>(), n, tmp.as<uint32_t>(), c->sm_count, st);
+  if (values) rsort::sort_pairs(dk, dv, kb.as<uint64_t>(), vb.as<uint32_t>(), n, tmp.as<uint32_t>(), c->sm_count, st);
+  else rsort::sort_keys(dk, kb.as<uint64_t>(), n, tmp.as<uint32_t>(), c->sm_count, st, 0, rsort::PASSES);
   TK_BC(cudaGetLastError());
   if (!kd) TK_BC(cudaMemcpyAsync(keys, dk, n * 8, cudaMemcpyDeviceToHost, st));
   if (!vd) TK_BC(cudaMemcpyAsync(values, dv, n * 4, cudaMemcpyDeviceToHost, st));
@@ -1414,7 +1452,7 @@ int tknn_morton_codes(tknn_ctx* c, const float* xyz, uint64_t n, int dim, int st
   TK_B(ensure(c, dob, sizeof(ob)));
   TK_BC(cudaMemcpyAsync(dob.p, ob, sizeof(ob), cudaMemcpyHostToDevice, st));
   lbvh::morton_kernel<<<blocks_for(n, lbvh::THREADS), lbvh::THREADS, 0, st>>>(d_xyz, n, dim, stride_floats, dob.as<uint32_t>(), 21,
-                                                                             0, d_keys, vals.as<uint32_t>());
+                                                                             0, 0, d_keys, vals.as<uint32_t>());
   TK_BC(cudaGetLastError());
   if (!out_dev) TK_BC(cudaMemcpyAsync(codes_out, d_keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   TK_BC(cudaStreamSynchronize(st));

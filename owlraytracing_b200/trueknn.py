@@ -100,7 +100,7 @@ class TrueKNN:
         "approx_filter": _lib.OPT_APPROX_FILTER, "output_chunks": _lib.OPT_OUTPUT_CHUNKS,
         "file_order_chunks": _lib.OPT_FILE_ORDER_CHUNKS, "morton_bits": _lib.OPT_MORTON_BITS,
         "tie_pruning": _lib.OPT_TIE_PRUNING, "warp_round_max": _lib.OPT_WARP_ROUND_MAX, "curve": _lib.OPT_CURVE,
-        "speculative_max": _lib.OPT_SPECULATIVE_MAX, "sparse_team": _lib.OPT_SPARSE_TEAM,
+        "speculative_max": _lib.OPT_SPECULATIVE_MAX, "sparse_team": _lib.OPT_SPARSE_TEAM, "sort_mode": _lib.OPT_SORT_MODE,
     }
 
     def set_option(self, name: str, value: int):
@@ -350,9 +350,9 @@ class TrueKNN:
         return int(a.value), int(b.value)
 
     # ---- introspection (tests / bench) ----
-    def sort_pairs(self, keys, values):
+    def sort_pairs(self, keys, values=None):
         n = int(keys.shape[0])
-        self._check(self._L.tknn_sort_pairs(self._h, self._in(keys), self._in(values), n))
+        self._check(self._L.tknn_sort_pairs(self._h, self._in(keys), self._in(values) if values is not None else None, n))
         return keys, values
 
     def get_bvh(self):

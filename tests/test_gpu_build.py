@@ -38,6 +38,35 @@ def test_onesweep_sort_extreme_keys(knn):
     assert (k2 == keys[order]).all() and (v2 == order.astype(np.uint32)).all()
 
 
+@pytest.mark.parametrize("n", [1, 33, 4096, 4097, 250_001])
+def test_onesweep_keys_only(knn, n):
+    """The keys-only kernel variant (the builder's packed (code, index) keys) over all 64 key bits."""
+    rng = np.random.default_rng(n + 7)
+    keys = rng.integers(0, 2**64 - 1, n, dtype=np.uint64)
+    keys[: n // 3] = keys[0]  # a long run of equal keys
+    k2, _ = knn.sort_pairs(keys.copy())
+    assert (k2 == np.sort(keys)).all()
+
+
+@pytest.mark.parametrize("cloud", ["uniform", "lidar", "dups"])
+def test_packed_sort_equals_pair_sort(knn, cloud):
+    """TKNN_OPT_SORT_MODE: packed (code << index bits | index) keys sorted keys-only put the points in the same order
+    as the stable (code, index) pair sort with the same number of code bits."""
+    n = 70_001
+    x = {"uniform": lambda: datasets.uniform(n, seed=3), "lidar": lambda: datasets.lidar_like(n, seed=3),
+         "dups": lambda: np.tile(datasets.uniform(701, seed=4), (100, 1))}[cloud]()
+    got = []
+    for mode in (0, 1):
+        knn.set_option("sort_mode", mode)
+        knn.set_option("morton_bits", 12)
+        knn.build(x)
+        nodes, pts, leaf_start = knn.get_bvh()
+        _walk(nodes, pts, leaf_start)
+        got.append((pts.copy(), leaf_start.copy()))
+    assert (got[0][0].view(np.int32) == got[1][0].view(np.int32)).all()
+    assert (got[0][1] == got[1][1]).all()
+
+
 def _walk(nodes, pts, leaf_start):
     """Returns per-node (lo, hi, count) computed from the leaves; asserts stored child boxes are exact."""
     refs = nodes.view(np.int32)
