@@ -160,6 +160,8 @@ TKNN_API int tknn_build(tknn_ctx* ctx, const float* xyz, uint64_t n, int dim, in
  * start_radius > 0: round 1 searches the closed ball of that radius, unresolved queries double it
  * (hostCode.cpp:323); start_radius <= 0: estimated from a sample (Util/random_sample.py's role);
  * start_radius = +inf: one unbounded round.  idx_out/dist_out: n*k each, rows in build order.
+ * dist_out may be NULL (tknn_search and tknn_search_shard): indices only — with host outputs that halves the
+ * device->host copy, which bounds the end-to-end time of a large search.
  * k must satisfy 1 <= k <= min(n-1, TKNN_MAX_K) (the reference never terminates for k > n-1). */
 TKNN_API int tknn_search(tknn_ctx* ctx, int k, float start_radius, int32_t* idx_out, float* dist_out);
 

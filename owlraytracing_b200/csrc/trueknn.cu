@@ -533,7 +533,7 @@ int tknn::host::search_range(tknn_ctx* c, int k, float start_radius, uint64_t q_
   if ((uint64_t)k > c->n - 1) return fail(c, TKNN_EINVAL, "k = %d > n - 1 = %llu: fewer than k neighbours exist", k,
                                           (unsigned long long)(c->n - 1));
   if (std::isnan(start_radius)) return fail(c, TKNN_EINVAL, "start_radius is NaN");
-  if (!idx_out || !dist_out) return fail(c, TKNN_EINVAL, "null output array");
+  if (!idx_out) return fail(c, TKNN_EINVAL, "null output array");
   if (c->ids_in_w && row_mode == 0)
     return fail(c, TKNN_ESTATE, "this BVH carries caller-chosen point ids (point-partitioned build): rows in build order do not exist");
   reset_search_stats(c);
@@ -541,7 +541,9 @@ int tknn::host::search_range(tknn_ctx* c, int k, float start_radius, uint64_t q_
   c->stats.k = k;
   uint32_t* sc = c->scalars.as<uint32_t>();
 
-  const bool idx_dev = is_device_ptr(idx_out), dist_dev = is_device_ptr(dist_out);
+  // dist_out == nullptr: indices only — the distances stay in device scratch and are never copied (half the
+  // device->host bytes of a host-output call; a distance is recomputable from its index)
+  const bool idx_dev = is_device_ptr(idx_out), dist_dev = !dist_out || is_device_ptr(dist_out);
   const bool qid_dev = qid_out ? is_device_ptr(qid_out) : true;
   int32_t* d_idx = idx_out;
   float* d_dist = dist_out;
@@ -552,7 +554,7 @@ int tknn::host::search_range(tknn_ctx* c, int k, float start_radius, uint64_t q_
     if (!idx_dev) d_idx = c->stage_idx.as<int32_t>();
     if (qid_out && !qid_dev) d_qid = c->stage_idx.as<int32_t>() + out_elems;
   }
-  if (!dist_dev) {
+  if (!dist_dev || !dist_out) {
     TK_TRY(ensure(c, c->stage_dist, out_elems * sizeof(float)));
     d_dist = c->stage_dist.as<float>();
   }

@@ -171,16 +171,18 @@ class TrueKNN:
         self._like = points
         return self
 
-    def search(self, k: int, start_radius: float = 0.0, out=None):
-        """All-points kNN. Returns (idx [n,k] int32, dist [n,k] float32), rows in build order."""
+    def search(self, k: int, start_radius: float = 0.0, out=None, indices_only: bool = False):
+        """All-points kNN. Returns (idx [n,k] int32, dist [n,k] float32), rows in build order.
+        indices_only (or out = (idx, None)): dist_out = NULL — no distances are returned or copied."""
         if out is None:
             idx = self._out(self._like, self.n, k, np.int32)
-            dist = self._out(self._like, self.n, k, np.float32)
+            dist = None if indices_only else self._out(self._like, self.n, k, np.float32)
         else:
             idx, dist = out
         _check_dtype(idx, np.int32, "idx_out")
-        _check_dtype(dist, np.float32, "dist_out")
-        self._check(self._L.tknn_search(self._h, int(k), C.c_float(start_radius), _ptr(idx), _ptr(dist)))
+        if dist is not None:
+            _check_dtype(dist, np.float32, "dist_out")
+        self._check(self._L.tknn_search(self._h, int(k), C.c_float(start_radius), _ptr(idx), _ptr(dist) if dist is not None else None))
         return idx, dist
 
     def shard_capacity(self, n_shards: int) -> int:

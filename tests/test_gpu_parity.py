@@ -591,3 +591,25 @@ def test_sparse_round_kernels_agree(oracle, team, cloud, k):
         st = t.stats()
         assert_knn_equal(idx, dist, *ref, f"sparse_team={team} {cloud} k={k}")
         assert st["rounds"] >= 2 and 64 < st["round_queries"][1] * 1 and st["round_queries"][1] * 8 <= x.shape[0]
+
+
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_indices_only_output(knn, oracle, where):
+    """dist_out = NULL (tknn_search): the same indices, no distances copied; the sliced host-output path included."""
+    import torch
+
+    n, k = 300_000, 7
+    x = datasets.uniform(n, seed=11)
+    ref_idx, _ = oracle.knn_kdtree(x, k)
+    if where == "host":
+        knn.build(x)
+        idx, dist = knn.search(k, indices_only=True)
+        assert dist is None
+        assert knn.stats()["d2h_bytes"] == n * k * 4
+        assert (idx == ref_idx).all()
+    else:
+        xd = torch.from_numpy(x).cuda()
+        knn.build(xd)
+        idx, dist = knn.search(k, indices_only=True)
+        assert dist is None and idx.is_cuda
+        assert (idx.cpu().numpy() == ref_idx).all()
