@@ -630,6 +630,27 @@ def run_e2e(args, t, torch, dist, dev, stream, world, rank, wl, cfg, n_points, c
     e_ms, wall_ms = max_over_ranks([max(ev0.elapsed_time(ev1), 0.0), wall_ms])
     e_ms /= e2e_steps
     ph = max_over_ranks([phases[p] / e2e_steps for p in ("h2d_ms", "allgather_ms", "build_ms", "search_ms", "d2h_ms")])
+    indices_only = None
+    if world == 1 and not partition and not args.e2e_shard_api:
+        # the same step with dist_out = NULL: only the neighbour indices leave the device (half the D2H bytes)
+        def io_step():
+            t.build(my_slice.numpy())
+            t.search(k, args.start_radius, out=(full_np[0], None))
+            return t.stats()
+        io_step()
+        torch.cuda.synchronize()
+        io0, io1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        io0.record(stream)
+        for _ in range(e2e_steps):
+            ios = io_step()
+        io1.record(stream)
+        torch.cuda.synchronize()
+        io_ms = io0.elapsed_time(io1) / e2e_steps
+        indices_only = {"value": total_queries / (io_ms * 1e-3), "unit": "queries/s", "ms_per_step": io_ms,
+                        "h2d_bytes_per_step": int(my_slice.shape[0] * 12), "d2h_bytes_per_step": int(ios["d2h_bytes"]),
+                        "api": "tknn_build + tknn_search(dist_out = NULL): neighbour indices only, rows in file order",
+                        "note": "not the headline: the reference's output is indices AND distances (e2e.value); reported because "
+                                "the device->host copy of the rows bounds the step and a distance is recomputable from its index"}
     if partition:
         api = "tknn_partition_build + tknn_partition_search (host arrays)"
     elif world == 1 and not args.e2e_shard_api:
@@ -645,7 +666,8 @@ def run_e2e(args, t, torch, dist, dev, stream, world, rank, wl, cfg, n_points, c
                            "the next slice's search, so search_ms includes the overlapped copies and d2h_ms is the exposed tail",
             "h2d_note": ("per rank: its 1/N slice of the points (pinned); one ncclAllGather inside the library replicates the cloud"
                          if world > 1 and not partition else "per rank: its points (pinned)"),
-            "steps": e2e_steps, "includes": "H2D points (pinned) + build + search (all rounds) + D2H results (pinned)", "api": api}
+            "steps": e2e_steps, "includes": "H2D points (pinned) + build + search (all rounds) + D2H results (pinned)", "api": api,
+            **({"indices_only": indices_only} if indices_only else {})}
 
 
 def main():

@@ -87,6 +87,8 @@ int popc_scan(tknn_ctx* c, const uint32_t* words, uint64_t nw, uint32_t* offsets
 // ---------------------------------------------------------------------------------------------
 // the round driver (shared by search / shard / query / estimator)
 // ---------------------------------------------------------------------------------------------
+int fetch_words(tknn_ctx* c, const uint32_t* a, int na, const uint32_t* b, int nb, uint32_t* host_out);  // below
+
 struct Job {
   const float4* queries = nullptr;
   const int32_t* self_ids = nullptr;
@@ -281,9 +283,9 @@ int run_rounds(tknn_ctx* c, const Job& job, int* launches_io) {
   // {unresolved count, radius} in one read-back: the one host decision of a round (hostCode.cpp:310-330)
   auto read_back = [&](uint32_t* count) -> int {
     struct { uint32_t total; float r; } h = {0, 0.f};
-    TK_CUDA(c, cudaMemcpyAsync(&h.total, sc + SC_TOTAL, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    if (!radius_known) TK_CUDA(c, cudaMemcpyAsync(&h.r, job.r_dev, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    TK_CUDA(c, cudaStreamSynchronize(c->stream));
+    static_assert(sizeof(h) == 2 * sizeof(uint32_t), "mailbox layout");
+    TK_TRY(fetch_words(c, sc + SC_TOTAL, 1, reinterpret_cast<const uint32_t*>(job.r_dev), radius_known ? 0 : 1,
+                       reinterpret_cast<uint32_t*>(&h)));
     *count = h.total;
     if (!radius_known) { radius = h.r; radius_known = true; if (job.r_host) *job.r_host = h.r; }
     return TKNN_OK;
@@ -475,10 +477,36 @@ int hilbert_levels(uint64_t n, int bits, int forced = 0) {
 
 int check_ctx(tknn_ctx* c) { return c ? TKNN_OK : TKNN_EINVAL; }
 
+// out[0 .. na) = a[0 .. na), out[na .. na + nb) = b[0 .. nb): the mailbox writer (ctx.cuh)
+static __global__ void mailbox_kernel(const uint32_t* __restrict__ a, int na, const uint32_t* __restrict__ b, int nb,
+                                      volatile uint32_t* out) {
+  for (int i = 0; i < na; ++i) out[i] = a[i];
+  for (int i = 0; i < nb; ++i) out[na + i] = b[i];
+  __threadfence_system();
+}
+
+// Brings na + nb (<= 16) device words to the host and waits for the stream.  With host outputs the bulk result copies of
+// the previous slice occupy the device->host copy engine for milliseconds; a 4-byte cudaMemcpyAsync on the compute stream
+// would queue behind them and stall the round loop (measured: cfg2's four file-order slices searched in 15.2 ms with
+// idx + dist copies in flight against 12.6 ms with half the bytes).  A kernel's stores to mapped host memory do not.
+int fetch_words(tknn_ctx* c, const uint32_t* a, int na, const uint32_t* b, int nb, uint32_t* host_out) {
+  if (na + nb > 16 || na < 0 || nb < 0) return fail(c, TKNN_EINVAL, "internal: mailbox overflow");
+  if (c->mailbox_h) {
+    mailbox_kernel<<<1, 1, 0, c->stream>>>(a, na, b, nb, c->mailbox_d);
+    TK_CUDA(c, cudaGetLastError());
+    TK_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < na + nb; ++i) host_out[i] = c->mailbox_h[i];
+    return TKNN_OK;
+  }
+  if (na) TK_CUDA(c, cudaMemcpyAsync(host_out, a, na * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (nb) TK_CUDA(c, cudaMemcpyAsync(host_out + na, b, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  TK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return TKNN_OK;
+}
+
 int read_error_flag(tknn_ctx* c) {
   uint32_t e[2] = {0, 0};  // SC_ERROR, SC_QBAD
-  TK_CUDA(c, cudaMemcpyAsync(e, c->scalars.as<uint32_t>() + SC_ERROR, sizeof(e), cudaMemcpyDeviceToHost, c->stream));
-  TK_CUDA(c, cudaStreamSynchronize(c->stream));
+  TK_TRY(fetch_words(c, c->scalars.as<uint32_t>() + SC_ERROR, 2, nullptr, 0, e));
   if (e[0]) return fail(c, TKNN_ECUDA, "traversal stack overflow (BVH deeper than %d)", STACK_DEPTH);
   if (e[1]) return fail(c, TKNN_EINVAL, "non-finite coordinate in the query points");
   return TKNN_OK;
@@ -593,6 +621,11 @@ int tknn::host::search_range(tknn_ctx* c, int k, float start_radius, uint64_t q_
   const bool host_out = !idx_dev || !dist_dev || (qid_out && !qid_dev);
   const int chunks = (row_mode == 1 && host_out && c->output_chunks > 1 && nq >= (1u << 18))
                          ? (int)std::min<uint64_t>((uint64_t)c->output_chunks, groups) : 1;
+  // file-order slices: the device->host link moves the rows of a slice about as fast as a slice of that sparsity is
+  // searched, so the step ends one slice-search after the link could have started: 5 slices with distances (cfg2: 21.2 /
+  // 20.6 / 20.3 / 20.9 / 21.8 ms end to end with 3 / 4 / 5 / 6 / 8), 2 when only indices leave the device (17.9 / 16.5 / 16.9
+  // ms with 1 / 2 / 3)
+  const int fo_chunks = c->file_order_chunks > 0 ? c->file_order_chunks : (dist_out ? 5 : 2);
   if (chunks > 1) {
     while ((int)c->chunk_ev.size() < chunks) {
       cudaEvent_t e;
@@ -632,11 +665,11 @@ int tknn::host::search_range(tknn_ctx* c, int k, float start_radius, uint64_t q_
     // the caller's stream must not run ahead of the copies
     TK_CUDA(c, cudaEventRecord(c->chunk_ev[0], c->copy_stream));
     TK_CUDA(c, cudaStreamWaitEvent(c->stream, c->chunk_ev[0], 0));
-  } else if (row_mode == 0 && host_out && c->file_order_chunks > 1 && nq == c->n && nq >= (1u << 18)) {
+  } else if (row_mode == 0 && host_out && fo_chunks > 1 && nq == c->n && nq >= (1u << 18)) {
     // File-order rows: slice the queries by ORIGINAL index so that each slice's rows are one contiguous,
     // final block of the output.  A slice is every C-th point of the cloud in Morton order, so its groups
     // are C times less dense in space (costlier per query) — the price of overlapping the result copy.
-    const int fc = c->file_order_chunks;
+    const int fc = fo_chunks;
     while ((int)c->chunk_ev.size() < fc) {
       cudaEvent_t e;
       TK_CUDA(c, cudaEventCreate(&e));
@@ -736,6 +769,18 @@ int tknn_create(int device, tknn_ctx** out) {
     if (cudaEventCreate(&ev) != cudaSuccess) { delete c; return TKNN_ECUDA; }
   if (cudaMalloc(&c->scalars.p, SC_WORDS * sizeof(uint32_t)) != cudaSuccess) { delete c; return TKNN_ENOMEM; }
   c->scalars.bytes = SC_WORDS * sizeof(uint32_t);
+  {  // the mailbox is an optimisation: without mapped memory fetch_words falls back to small copies
+    void* h = nullptr;
+    void* d = nullptr;
+    if (cudaHostAlloc(&h, 16 * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess &&
+        cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
+      c->mailbox_h = static_cast<uint32_t*>(h);
+      c->mailbox_d = static_cast<uint32_t*>(d);
+    } else {
+      if (h) cudaFreeHost(h);
+      cudaGetLastError();
+    }
+  }
   *out = c;
   return TKNN_OK;
 }
@@ -757,6 +802,7 @@ int tknn_destroy(tknn_ctx* c) {
   for (auto& ev : c->chunk_ev) cudaEventDestroy(ev);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->mailbox_h) cudaFreeHost(c->mailbox_h);
   delete c;
   return TKNN_OK;
 }
@@ -817,7 +863,7 @@ int tknn_set_option(tknn_ctx* c, int key, int64_t value) {
       c->curve_levels = value > 100 ? (int)value - 100 : 0;
       return TKNN_OK;
     case TKNN_OPT_FILE_ORDER_CHUNKS:
-      if (value < 1 || value > 64) return fail(c, TKNN_EINVAL, "file-order chunks outside [1, 64]");
+      if (value < 0 || value > 64) return fail(c, TKNN_EINVAL, "file-order chunks outside [0, 64]");
       c->file_order_chunks = (int)value;
       return TKNN_OK;
     case TKNN_OPT_OUTPUT_CHUNKS:
@@ -952,11 +998,10 @@ int tknn::host::build_core(tknn_ctx* c, const float* xyz, uint64_t n, int dim, i
       skeys, n, c->leaf_size, c->leaf_policy, force_split, ballots.as<uint32_t>());
   launches += 1;
   TK_B(popc_scan(c, ballots.as<uint32_t>(), nw, c->offsets.as<uint32_t>(), &launches));
-  uint32_t m = 0;
-  uint32_t bad[1] = {0};
-  TK_BC(cudaMemcpyAsync(&m, sc + SC_TOTAL, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  TK_BC(cudaMemcpyAsync(bad, sc + SC_BOUNDS + 6, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  TK_BC(cudaStreamSynchronize(st));  // the leaf count sizes every later launch
+  uint32_t mb[2] = {0, 0};
+  TK_B(fetch_words(c, sc + SC_TOTAL, 1, sc + SC_BOUNDS + 6, 1, mb));  // the leaf count sizes every later launch
+  const uint32_t m = mb[0];
+  const uint32_t bad[1] = {mb[1]};
   if (bad[0]) { cleanup(); return fail(c, TKNN_EINVAL, "non-finite coordinate in the input points"); }
   if (m < 2) { cleanup(); return fail(c, TKNN_ECUDA, "internal: leaf cut produced %u leaves", m); }
   TK_B(ensure(c, c->leaf_start, (size_t)(m + 1) * sizeof(uint32_t)));
@@ -993,10 +1038,10 @@ int tknn::host::build_core(tknn_ctx* c, const float* xyz, uint64_t n, int dim, i
   ++launches;
   TK_BC(cudaGetLastError());
   TK_BC(cudaEventRecord(c->ev[7], st));
-  TK_BC(cudaMemcpyAsync(c->scene_box, sc + SC_SCENE, 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  uint32_t dupleaf = 0;
-  TK_BC(cudaMemcpyAsync(&dupleaf, sc + SC_DUPLEAF, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  TK_BC(cudaStreamSynchronize(st));
+  uint32_t tail[7] = {0, 0, 0, 0, 0, 0, 0};
+  TK_B(fetch_words(c, sc + SC_SCENE, 6, sc + SC_DUPLEAF, 1, tail));
+  std::memcpy(c->scene_box, tail, 6 * sizeof(float));
+  const uint32_t dupleaf = tail[6];
   cleanup();
 #undef TK_B
 #undef TK_BC
@@ -1065,8 +1110,9 @@ int tknn_estimate_start_radius(tknn_ctx* c, int k, float* radius_out) {
   ScopedDevice sd(c->device);
   int launches = 0;
   TK_TRY(estimate_radius_device(c, c->pts.as<float4>(), 0, c->n, nullptr, 1, k, &launches));
-  TK_CUDA(c, cudaMemcpyAsync(radius_out, c->scalars.as<uint32_t>() + SC_QUANTILE, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  TK_CUDA(c, cudaStreamSynchronize(c->stream));
+  uint32_t rb = 0;
+  TK_TRY(fetch_words(c, c->scalars.as<uint32_t>() + SC_QUANTILE, 1, nullptr, 0, &rb));
+  std::memcpy(radius_out, &rb, sizeof(float));
   return TKNN_OK;
 }
 
