@@ -312,8 +312,24 @@ __host__ __device__ inline size_t klist_bytes(int k) {
   return (b + 15) / 16 * 16;
 }
 
+// Sibling leaves together (TKNN_PAIR_LEAVES): when BOTH children of a node are leaves and the group wants both, the two
+// leaves are staged side by side, filtered into two masks and inserted in ONE divergent loop.  The insert loop runs
+// max-over-lanes(survivors) iterations of ~90 warp instructions at ~5 active lanes — 41 % of the dense kernel's
+// instructions — and the lanes that find survivors in two sibling leaves are mostly different lanes, so one loop over both
+// is shorter than two loops; the price is that the second leaf is filtered against the bound as it was before the first
+// one tightened it (its stale survivors fail the re-test at insert time).  1: ascending-list kernel only (k <= 24);
+// 2: heap kernel too (+768 B of staging per warp: one resident warp fewer at k = 64).
+#ifndef TKNN_PAIR_LEAVES
+#define TKNN_PAIR_LEAVES 1
+#endif
+__host__ __device__ constexpr bool pair_leaves(bool heap) { return TKNN_PAIR_LEAVES >= 2 || (TKNN_PAIR_LEAVES == 1 && !heap); }
+// points staged per warp = axis stride of the SoA staging area
+__host__ __device__ constexpr int stage_pts(bool heap) { return pair_leaves(heap) ? 2 * MAX_LEAF : MAX_LEAF; }
+
 __host__ __device__ inline size_t smem_per_warp(int k) {
-  return klist_bytes(k) + 2 * MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int);
+  const int ns = stage_pts(k > LIST_MAX_K);
+  return klist_bytes(k) + (size_t)ns * sizeof(float4) + (ns > MAX_LEAF ? 3 * ns * sizeof(float) : MAX_LEAF * sizeof(float4)) +
+         STACK_DEPTH * sizeof(int);
 }
 
 // ---- index-aware pruning of exact ties ----------------------------------------------------------
@@ -375,10 +391,11 @@ __device__ __forceinline__ float2 dist2_x2(float2 qx, float2 qy, float2 qz, floa
 }
 
 // bit i of the result: point j0 + i of the staged leaf is within `bound` of the lane's query
+template <int NS = MAX_LEAF>  // NS = axis stride of the staging area (stage_pts)
 __device__ __forceinline__ uint32_t filter4(const float* sx, int j0, float2 qx, float2 qy, float2 qz, float bound) {
   const float4 X = *reinterpret_cast<const float4*>(sx + j0);
-  const float4 Y = *reinterpret_cast<const float4*>(sx + MAX_LEAF + j0);
-  const float4 Z = *reinterpret_cast<const float4*>(sx + 2 * MAX_LEAF + j0);
+  const float4 Y = *reinterpret_cast<const float4*>(sx + NS + j0);
+  const float4 Z = *reinterpret_cast<const float4*>(sx + 2 * NS + j0);
   const float2 a = dist2_x2(qx, qy, qz, make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y));
   const float2 b = dist2_x2(qx, qy, qz, make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w));
   uint32_t m = 0;
@@ -414,7 +431,7 @@ __device__ __forceinline__ uint32_t filter4(const float* sx, int j0, float2 qx, 
 // tie pruning (chosen by the host when the build found leaves of coincident points).
 // HEAP: k > LIST_MAX_K (compile-time, so the small-k kernel does not carry the heap code).
 template <int MODE, bool COUNT, int VARIANT, bool HEAP>
-static __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
+static __global__ void __launch_bounds__(256, HEAP ? 1 : 5) traverse_kernel(const Params P) {
   constexpr bool APPROX = VARIANT == 1;
   constexpr bool TIES = VARIANT == 2 && MODE == MODE_KNN;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -422,12 +439,14 @@ static __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
   const int k = P.k;
   constexpr bool heap = HEAP;
   unsigned char* wbase = smem + (size_t)warp * smem_per_warp(MODE == MODE_KNN ? k : 0);
+  constexpr int NS = stage_pts(HEAP);  // staged points = SoA axis stride (64 with sibling-leaf pairs)
+  constexpr bool PAIR = pair_leaves(HEAP) && MODE == MODE_KNN && VARIANT != 1;
   float4* stage = reinterpret_cast<float4*>(wbase);
-  int* stack = reinterpret_cast<int*>(wbase + MAX_LEAF * sizeof(float4));
+  int* stack = reinterpret_cast<int*>(wbase + NS * sizeof(float4));
   constexpr int S = HEAP ? 32 : KLS;  // slot stride of the k-lists (keys)
-  uint64_t* H = reinterpret_cast<uint64_t*>(wbase + MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int)) + lane;
+  uint64_t* H = reinterpret_cast<uint64_t*>(wbase + NS * sizeof(float4) + STACK_DEPTH * sizeof(int)) + lane;
   // second staging array (relative coordinates + squared norm) for the pre-filter, behind the k-list
-  float4* stage2 = reinterpret_cast<float4*>(wbase + MAX_LEAF * sizeof(float4) + STACK_DEPTH * sizeof(int) +
+  float4* stage2 = reinterpret_cast<float4*>(wbase + NS * sizeof(float4) + STACK_DEPTH * sizeof(int) +
                                              klist_bytes(MODE == MODE_KNN ? k : 0));
   float* soa = reinterpret_cast<float*>(stage2);  // exact filter: the leaf's x[32] | y[32] | z[32] (same region)
 
@@ -469,6 +488,35 @@ static __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
       qq = __fmaf_rn(qrz, qrz, __fmaf_rn(qry, qry, __fmul_rn(qrx, qrx)));
     }
 
+    // one candidate of the staged leaf (or leaf pair): exact distance, self test, bound test, insert; the bound tightens
+    auto try_insert = [&](int j) {
+      const float4 p = stage[j];
+      const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+      const int pid = __float_as_int(p.w);
+      if (pid != self && d <= bound) {
+        const uint64_t key = make_key(d, pid);
+        if (!HEAP && TKNN_WORST_REG == 2) {
+          // d <= bound holds: the key beats the worst entry unless it TIES its distance with a higher index
+          if (cnt < k || d < bound || pid < key_idx(kl_worst<S>(H, k, heap))) {
+            const uint64_t tail = list_insert<S>(H, cnt, k, key);
+            if (cnt == k) bound = key_d2(tail);
+            if (COUNT) c_ins += 1;
+          }
+        } else if (!HEAP && TKNN_WORST_REG) {
+          // (d, pid) < (bound, widx): the worst entry's key lives in registers (bound = its d2)
+          if (cnt < k || d < bound || pid < widx) {
+            const uint64_t tail = list_insert<S>(H, cnt, k, key);
+            if (cnt == k) { bound = key_d2(tail); widx = key_idx(tail); }
+            if (COUNT) c_ins += 1;
+          }
+        } else if (cnt < k || key < kl_worst<S>(H, k, heap)) {
+          kl_insert<true, S>(H, cnt, k, key, heap);
+          if (cnt == k) bound = key_d2(kl_worst<S>(H, k, heap));
+          if (COUNT) c_ins += 1;
+        }
+      }
+    };
+
     int sp = 0;
     int node = 0;
     for (;;) {
@@ -486,167 +534,118 @@ static __global__ void __launch_bounds__(256) traverse_kernel(const Params P) {
         bool swap = false;
         if (cnt0 > 0 && cnt1 > 0)
           swap = __popc(__ballot_sync(FULL_MASK, d1 < d0)) > __popc(__ballot_sync(FULL_MASK, d0 < d1));
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          const bool second = (c == 1) != swap;  // false: child 0, true: child 1
-          const int lcount = second ? cnt1 : cnt0;
-          if (lcount <= 0) continue;
+        // does the group want leaf child 0 / 1 (second)?  Evaluated against the bounds as they are NOW.
+        auto leaf_wanted = [&](bool second) -> bool {
+          if ((second ? cnt1 : cnt0) <= 0) return false;
           const float dc = second ? d1 : d0;
-          if (!__any_sync(FULL_MASK, dc <= bound)) continue;
+          if (!__any_sync(FULL_MASK, dc <= bound)) return false;
           if (TIES && !__any_sync(FULL_MASK, dc < bound)) {  // only exact ties: can any of them win?
             const int2 mi = __ldg(&P.node_min_idx[node]);
-            if (!child_wanted<MODE, S>(dc, bound, cnt, k, H, heap, second ? mi.y : mi.x)) continue;
+            return child_wanted<MODE, S>(dc, bound, cnt, k, H, heap, second ? mi.y : mi.x);
           }
-          const int start = second ? ref1 : ref0;
-          float cx = 0.f, cy = 0.f, cz = 0.f;
-          if (APPROX && MODE == MODE_KNN) {  // the group origin = lane 0's query (re-broadcast: saves 3 registers)
-            cx = __shfl_sync(FULL_MASK, q.x, 0); cy = __shfl_sync(FULL_MASK, q.y, 0); cz = __shfl_sync(FULL_MASK, q.z, 0);
-          }
-          if (lane < lcount) {
-            const float4 pl = __ldg(&P.pts[(uint64_t)(uint32_t)start + lane]);
-            stage[lane] = pl;
-            if (APPROX && MODE == MODE_KNN) {
-              const float rx = __fsub_rn(pl.x, cx), ry = __fsub_rn(pl.y, cy), rz = __fsub_rn(pl.z, cz);
-              stage2[lane] = make_float4(rx, ry, rz, __fmaf_rn(rz, rz, __fmaf_rn(ry, ry, __fmul_rn(rx, rx))));
-            } else {
-              soa[lane] = pl.x; soa[MAX_LEAF + lane] = pl.y; soa[2 * MAX_LEAF + lane] = pl.z;
-            }
-          } else if (!(APPROX && MODE == MODE_KNN)) {
-            soa[lane] = __int_as_float(0x7fc00000);  // NaN: the padded tail of the last chunk never passes
-          }
-          __syncwarp();
-          if (COUNT) { c_tests += valid ? lcount : 0; c_wleaves += 1; c_wpts += lcount; }
-          if (MODE == MODE_RANGE_COUNT) {
-            // every point within the radius, the query's own point included: it lies at distance 0 in the one
-            // leaf that holds it and is taken off again at emit time
+          return true;
+        };
+        // sibling leaves both wanted: one staging, two masks, ONE insert loop (TKNN_PAIR_LEAVES)
+        const bool pair = PAIR && cnt0 > 0 && cnt1 > 0 && leaf_wanted(false) && leaf_wanted(true);
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t mask_a = 0, mask_b = 0;  // survivors among staged points 0..31 / 32..63
+          if (pair) {
+            if (c == 1) break;
+            const float qnan = __int_as_float(0x7fc00000);
+            float4 pa = make_float4(qnan, 0.f, 0.f, 0.f), pb = pa;  // NaN x: a padded slot never passes the filter
+            if (lane < cnt0) pa = __ldg(&P.pts[(uint64_t)(uint32_t)ref0 + lane]);
+            if (lane < cnt1) pb = __ldg(&P.pts[(uint64_t)(uint32_t)ref1 + lane]);
+            stage[lane] = pa;
+            stage[MAX_LEAF + lane] = pb;
+            soa[lane] = pa.x; soa[NS + lane] = pa.y; soa[2 * NS + lane] = pa.z;
+            soa[MAX_LEAF + lane] = pb.x; soa[NS + MAX_LEAF + lane] = pb.y; soa[2 * NS + MAX_LEAF + lane] = pb.z;
+            __syncwarp();
+            if (COUNT) { c_tests += valid ? cnt0 + cnt1 : 0; c_wleaves += 2; c_wpts += cnt0 + cnt1; }
             const float2 qx2 = make_float2(q.x, q.x), qy2 = make_float2(q.y, q.y), qz2 = make_float2(q.z, q.z);
 #pragma unroll 1
-            for (int j0 = 0; j0 < lcount; j0 += 4) cnt += __popc(filter4(soa, j0, qx2, qy2, qz2, bound));
-          } else {
-            // filter: full chunks of 8 with compile-time bit positions, then the remainder one by one
-            uint32_t mask = 0;
-            int j0 = 0;
-            if (APPROX) {
-              const float tau = valid ? prefilter_tau(bound, qq) : -INFINITY;
-              for (; j0 + 8 <= lcount; j0 += 8) {
-                uint32_t m8 = 0;
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                  const float4 p = stage2[j0 + jj];
-                  const float t = __fmaf_rn(ax, p.x, __fmaf_rn(ay, p.y, __fmaf_rn(az, p.z, p.w)));
-                  if (t <= tau) m8 |= (1u << jj);
-                }
-                mask |= m8 << j0;
-              }
-              for (; j0 < lcount; ++j0) {
-                const float4 p = stage2[j0];
-                const float t = __fmaf_rn(ax, p.x, __fmaf_rn(ay, p.y, __fmaf_rn(az, p.z, p.w)));
-                if (t <= tau) mask |= (1u << j0);
-              }
-              if (COUNT) {  // audit: an exactly-passing pair the pre-filter rejected would be a wrong result
-                for (int j = 0; j < lcount; ++j) {
-                  const float4 p = stage[j];
-                  const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
-                  if (valid && d <= bound && !((mask >> j) & 1u)) c_viol += 1;
-                }
-              }
-            } else {
-              const float2 qx2 = make_float2(q.x, q.x), qy2 = make_float2(q.y, q.y), qz2 = make_float2(q.z, q.z);
-              for (; j0 + 8 <= lcount; j0 += 8) {
-                const uint32_t m8 = filter4(soa, j0, qx2, qy2, qz2, bound) | (filter4(soa, j0 + 4, qx2, qy2, qz2, bound) << 4);
-                mask |= m8 << j0;
-              }
+            for (int j0 = 0; j0 < cnt0; j0 += 4) mask_a |= filter4<NS>(soa, j0, qx2, qy2, qz2, bound) << j0;
 #pragma unroll 1
-              for (; j0 < lcount; j0 += 4)  // tail in chunks of 4, NaN-padded past the last point
-                mask |= filter4(soa, j0, qx2, qy2, qz2, bound) << j0;
+            for (int j0 = 0; j0 < cnt1; j0 += 4) mask_b |= filter4<NS>(soa + MAX_LEAF, j0, qx2, qy2, qz2, bound) << j0;
+          } else {
+            const bool second = (c == 1) != swap;  // false: child 0, true: child 1
+            if (!leaf_wanted(second)) continue;
+            const int lcount = second ? cnt1 : cnt0;
+            const int start = second ? ref1 : ref0;
+            float cx = 0.f, cy = 0.f, cz = 0.f;
+            if (APPROX && MODE == MODE_KNN) {  // the group origin = lane 0's query (re-broadcast: saves 3 registers)
+              cx = __shfl_sync(FULL_MASK, q.x, 0); cy = __shfl_sync(FULL_MASK, q.y, 0); cz = __shfl_sync(FULL_MASK, q.z, 0);
             }
-            // insert: only lanes with survivors do work; the bound tightens as they go
-#if TKNN_INSERT_LOOP == 1
-            // every lane walks its own survivors; the warp reconverges once, behind the loop (no vote per candidate)
-            while (mask) {
-              const int j = __ffs(mask) - 1;
-              mask &= mask - 1u;
-              const float4 p = stage[j];
-              const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
-              const int pid = __float_as_int(p.w);
-              if (pid != self && d <= bound) {
-                const uint64_t key = make_key(d, pid);
-                if (!HEAP && TKNN_WORST_REG == 2) {
-                  // d <= bound holds: the key beats the worst entry unless it TIES its distance with a higher index
-                  if (cnt < k || d < bound || pid < key_idx(kl_worst<S>(H, k, heap))) {
-                    const uint64_t tail = list_insert<S>(H, cnt, k, key);
-                    if (cnt == k) bound = key_d2(tail);
-                    if (COUNT) c_ins += 1;
+            if (lane < lcount) {
+              const float4 pl = __ldg(&P.pts[(uint64_t)(uint32_t)start + lane]);
+              stage[lane] = pl;
+              if (APPROX && MODE == MODE_KNN) {
+                const float rx = __fsub_rn(pl.x, cx), ry = __fsub_rn(pl.y, cy), rz = __fsub_rn(pl.z, cz);
+                stage2[lane] = make_float4(rx, ry, rz, __fmaf_rn(rz, rz, __fmaf_rn(ry, ry, __fmul_rn(rx, rx))));
+              } else {
+                soa[lane] = pl.x; soa[NS + lane] = pl.y; soa[2 * NS + lane] = pl.z;
+              }
+            } else if (!(APPROX && MODE == MODE_KNN)) {
+              soa[lane] = __int_as_float(0x7fc00000);  // NaN: the padded tail of the last chunk never passes
+            }
+            __syncwarp();
+            if (COUNT) { c_tests += valid ? lcount : 0; c_wleaves += 1; c_wpts += lcount; }
+            if (MODE == MODE_RANGE_COUNT) {
+              // every point within the radius, the query's own point included: it lies at distance 0 in the one
+              // leaf that holds it and is taken off again at emit time
+              const float2 qx2 = make_float2(q.x, q.x), qy2 = make_float2(q.y, q.y), qz2 = make_float2(q.z, q.z);
+#pragma unroll 1
+              for (int j0 = 0; j0 < lcount; j0 += 4) cnt += __popc(filter4<NS>(soa, j0, qx2, qy2, qz2, bound));
+            } else {
+              // filter: full chunks of 8 with compile-time bit positions, then the remainder in chunks of 4
+              int j0 = 0;
+              if (APPROX) {
+                const float tau = valid ? prefilter_tau(bound, qq) : -INFINITY;
+                for (; j0 + 8 <= lcount; j0 += 8) {
+                  uint32_t m8 = 0;
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) {
+                    const float4 p = stage2[j0 + jj];
+                    const float t = __fmaf_rn(ax, p.x, __fmaf_rn(ay, p.y, __fmaf_rn(az, p.z, p.w)));
+                    if (t <= tau) m8 |= (1u << jj);
                   }
-                } else if (!HEAP && TKNN_WORST_REG) {
-                  // (d, pid) < (bound, widx): the worst entry's key lives in registers (bound = its d2)
-                  if (cnt < k || d < bound || pid < widx) {
-                    const uint64_t tail = list_insert<S>(H, cnt, k, key);
-                    if (cnt == k) { bound = key_d2(tail); widx = key_idx(tail); }
-                    if (COUNT) c_ins += 1;
-                  }
-                } else if (cnt < k || key < kl_worst<S>(H, k, heap)) {
-                  kl_insert<true, S>(H, cnt, k, key, heap);
-                  if (cnt == k) bound = key_d2(kl_worst<S>(H, k, heap));
-                  if (COUNT) c_ins += 1;
+                  mask_a |= m8 << j0;
                 }
-              }
-            }
-#else
-            for (;;) {
-              unsigned pend = __ballot_sync(FULL_MASK, mask != 0u);
-              if (pend == 0u) break;
-              if (!HEAP && COOP_MAX_LANES > 0 && __popc(pend) <= COOP_MAX_LANES) {
-                // Few lanes hold candidates: the WARP inserts them, one (query, candidate) at a time (coop_insert).
-                // Nothing but `pend` lives across iterations: the owner lane keeps its own cnt / bound / mask.
-                __syncwarp();
-                do {
-                  const int src = __ffs(pend) - 1;
-                  const uint32_t smask = __shfl_sync(FULL_MASK, mask, src);
-                  const int j = __ffs(smask) - 1;
-                  if (lane == src) mask &= mask - 1u;
-                  if ((smask & (smask - 1u)) == 0u) pend &= pend - 1u;  // that was src's last candidate
-                  const float4 p = stage[j];
-                  const float d = dist2(__shfl_sync(FULL_MASK, q.x, src), __shfl_sync(FULL_MASK, q.y, src),
-                                        __shfl_sync(FULL_MASK, q.z, src), p.x, p.y, p.z);
-                  const int pid = __float_as_int(p.w);
-                  if (pid != __shfl_sync(FULL_MASK, self, src) && d <= __shfl_sync(FULL_MASK, bound, src)) {
-                    uint64_t worst = 0;
-                    bool ins;
-                    const int ncnt = coop_insert(H - lane + src, __shfl_sync(FULL_MASK, cnt, src), k, make_key(d, pid), lane, worst, ins);
-                    if (ins && lane == src) {
-                      cnt = ncnt;
-                      if (ncnt == k) bound = key_d2(worst);
-                      if (COUNT) c_ins += 1;
-                    }
-                    __syncwarp();
-                  }
-                } while (pend);
-                break;
-              }
-              if (mask) {
-                const int j = __ffs(mask) - 1;
-                mask &= mask - 1u;
-                const float4 p = stage[j];
-                const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
-                const int pid = __float_as_int(p.w);
-                if (pid != self && d <= bound) {
-                  const uint64_t key = make_key(d, pid);
-                  if (!HEAP && TKNN_WORST_REG) {
-                    if (cnt < k || d < bound || pid < widx) {
-                      const uint64_t tail = list_insert<S>(H, cnt, k, key);
-                      if (cnt == k) { bound = key_d2(tail); widx = key_idx(tail); }
-                      if (COUNT) c_ins += 1;
-                    }
-                  } else if (cnt < k || key < kl_worst<S>(H, k, heap)) {
-                    kl_insert<true, S>(H, cnt, k, key, heap);
-                    if (cnt == k) bound = key_d2(kl_worst<S>(H, k, heap));
-                    if (COUNT) c_ins += 1;
+                for (; j0 < lcount; ++j0) {
+                  const float4 p = stage2[j0];
+                  const float t = __fmaf_rn(ax, p.x, __fmaf_rn(ay, p.y, __fmaf_rn(az, p.z, p.w)));
+                  if (t <= tau) mask_a |= (1u << j0);
+                }
+                if (COUNT) {  // audit: an exactly-passing pair the pre-filter rejected would be a wrong result
+                  for (int j = 0; j < lcount; ++j) {
+                    const float4 p = stage[j];
+                    const float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+                    if (valid && d <= bound && !((mask_a >> j) & 1u)) c_viol += 1;
                   }
                 }
+              } else {
+                const float2 qx2 = make_float2(q.x, q.x), qy2 = make_float2(q.y, q.y), qz2 = make_float2(q.z, q.z);
+                for (; j0 + 8 <= lcount; j0 += 8) {
+                  const uint32_t m8 = filter4<NS>(soa, j0, qx2, qy2, qz2, bound) | (filter4<NS>(soa, j0 + 4, qx2, qy2, qz2, bound) << 4);
+                  mask_a |= m8 << j0;
+                }
+#pragma unroll 1
+                for (; j0 < lcount; j0 += 4)  // tail in chunks of 4, NaN-padded past the last point
+                  mask_a |= filter4<NS>(soa, j0, qx2, qy2, qz2, bound) << j0;
               }
             }
-#endif
+          }
+          if (MODE == MODE_KNN) {
+            // insert: only lanes with survivors do work; the bound tightens as they go.  Every lane walks its own survivors
+            // (a pair: those of its nearer leaf first) and the warp reconverges once, behind the loop.
+            int off_a = 0;
+            if (PAIR && d1 < d0) { const uint32_t t = mask_a; mask_a = mask_b; mask_b = t; off_a = MAX_LEAF; }
+            while (mask_a | mask_b) {
+              int j;
+              if (!PAIR || mask_a) { j = off_a + __ffs(mask_a) - 1; mask_a &= mask_a - 1u; }
+              else { j = (MAX_LEAF - off_a) + __ffs(mask_b) - 1; mask_b &= mask_b - 1u; }
+              try_insert(j);
+            }
           }
           __syncwarp();
         }

@@ -1,9 +1,18 @@
 #!/bin/bash
-# one gpurun call: tests + e2e sweeps after the mailbox read-back
+# one gpurun call: parity tests + A/B of the sibling-leaf pair path
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_build.py tests/test_gpu_parity.py -x -q 2>&1 | tail -3
-timeout 200 python tools/e2e_sweep.py 3 4 5 6 8 > gpurun_out/r2_e2e_mailbox.txt 2>&1
-timeout 200 python tools/e2e_sweep.py --idx-only 1 2 3 >> gpurun_out/r2_e2e_mailbox.txt 2>&1
-cat gpurun_out/r2_e2e_mailbox.txt
-timeout 100 python tools/ab.py cfg1 libtrueknn.so 2>&1 | cut -c1-400
+timeout 300 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -3
+OUT=gpurun_out/r2_ab_pair.jsonl
+: > $OUT
+timeout 200 python tools/ab.py cfg2 v_pair0.so libtrueknn.so >> $OUT 2>&1
+timeout 300 python tools/ab.py cfg3 v_pair0.so libtrueknn.so v_pair2.so >> $OUT 2>&1
+timeout 200 python tools/ab.py cfg4 v_pair0.so libtrueknn.so >> $OUT 2>&1
+python - <<'PY'
+import json
+for l in open('gpurun_out/r2_ab_pair.jsonl'):
+    try: d=json.loads(l)
+    except Exception: print(l[:300]); continue
+    if 'rc' in d: print(d); continue
+    print(d['workload'], d['lib'], 'search', d['search_ms'], 'kernels', d['kernel_ms'], 'ins/q', d['inserts_per_q'], 'tests/q', d['tests_per_q'], 'nodes/q', d['nodes_per_q'], d['brute_ok'], d['checksum'])
+PY
