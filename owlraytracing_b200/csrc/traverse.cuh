@@ -164,29 +164,19 @@ __device__ __forceinline__ void pheap_sift_root(uint64_t* A, int size, uint64_t 
 }
 #undef TKNN_MAX2
 
-// Insert iterations with at most this many lanes holding a candidate are done cooperatively (coop_insert): a
-// private insert iteration costs ~95 warp instructions whatever the number of lanes in it, a cooperative insert ~30
-// per candidate.  -DTKNN_COOP_MAX_LANES=0 switches the cooperative path off.
-// MEASURED AND REJECTED (profiles/r2_ab_coop_cfg2.jsonl, cfg2 round 1): off 7.48 ms, <= 2 lanes 7.98, <= 3 lanes 8.36,
-// <= 5 lanes 9.25, <= 8 lanes 10.57 ms.  A cooperative insert is a chain of dependent warp-wide steps (7 shuffles, two
-// shared-memory round trips, a ballot) with no overlap between candidates, while the private path lets every lane
-// with a candidate walk its own list at once; the 95-instruction average of a private iteration is dominated by the
-// many-lane iterations, a one-lane iteration is far cheaper than that.  Kept behind the macro (default 0 = off).
-#ifndef TKNN_COOP_MAX_LANES
-#define TKNN_COOP_MAX_LANES 0
-#endif
-constexpr int COOP_MAX_LANES = TKNN_COOP_MAX_LANES;
+// A warp-COOPERATIVE insert (lane i owns rank i of one query's list, rows padded to 33 keys) for iterations with few
+// lanes holding a candidate was measured and rejected in round 2 (profiles/r2_ab_coop_cfg2.jsonl, cfg2 round 1: off 7.48 ms,
+// <= 2 lanes 7.98, <= 3 lanes 8.36, <= 5 lanes 9.25, <= 8 lanes 10.57 ms): a chain of dependent warp-wide steps per candidate
+// with no overlap between candidates, while the private path lets every lane walk its own list at once.  The code was
+// removed when the leaf section was unified (git history: 5fc7c56).
 
 // ---- bounded ASCENDING list of u64 keys in shared memory (slot s of lane l at L[s * S + l]) ----
 // Candidates arrive roughly nearest-first, so a new key usually lands near the tail: the backward
 // shift is short, and the list needs no heap-sort at emit time.  Precondition: cnt < k or key < L[k-1].
 // L points at a SENTINEL slot holding 0 (<= every key); entries live in slots 1..k.  The sentinel ends
 // the backward walk without a bounds test, so the loop unrolls to 5 instructions per step.
-// S = slot stride in keys: 32 (one 256-byte row per slot), or KLS = 33 in the cooperative kernel, where a row is
-// padded by one key so that the k slots of ONE lane fall into distinct banks (2 s mod 32): the warp can then read or
-// shift a single query's whole list in one conflict-free access (coop_insert below), while the per-lane accesses
-// (32 consecutive keys of one slot) stay conflict-free too.
-constexpr int KLS = COOP_MAX_LANES > 0 ? 33 : 32;
+// S = slot stride in keys: 32 (one 256-byte row per slot; the 32 lanes of a warp touch 32 consecutive keys: conflict-free).
+constexpr int KLS = 32;
 
 // Returns the key left in the slot that was filled, i.e. the list's new LAST entry — the new worst once the list is
 // full — so the caller keeps the bound and the worst index in registers instead of re-reading them.
@@ -223,29 +213,6 @@ __device__ __forceinline__ uint64_t list_insert(uint64_t* L, int& cnt, int k, ui
     *(p - 3 * S) = d;
     p -= 4 * S;
   }
-}
-
-// ---- cooperative insert: the whole warp works on ONE query's list ------------------------------------------
-// Most insert iterations of the dense kernel have one or two lanes with a candidate (a leaf away from a query's own
-// leaf improves few of the 32 lists), and a lane's private shift loop then runs at 1-2 of 32 lanes: 36 % of all warp
-// instructions on cfg2 (profiles/r2_traverse_cfg2_v9_regions.txt).  Here lane i owns rank i of the list of lane
-// `src`: one conflict-free load of the list (stride KLS), one ballot for the position, one predicated store for the
-// shift, one for the key — the same ~25 instructions whatever the shift length.  All arguments are warp-uniform;
-// Ls = sentinel slot of src's list.  Returns the updated count; `worst` receives the rank-(k-1) key once the list is
-// full.  Keys are distinct (distinct indices), the list ascends, k <= LIST_MAX_K < 32.
-__device__ __forceinline__ int coop_insert(uint64_t* Ls, int cnt, int k, uint64_t key, int lane, uint64_t& worst, bool& inserted) {
-  const uint64_t e = lane < cnt ? Ls[(lane + 1) * KLS] : ~0ull;  // rank `lane` (ranks past the count compare high)
-  const int pos = __popc(__ballot_sync(FULL_MASK, e < key));     // entries smaller than the key = its rank
-  inserted = pos < k;
-  if (!inserted) return cnt;                                     // a full list whose worst entry beats the key
-  const int ncnt = cnt < k ? cnt + 1 : k;
-  if (lane >= pos && lane + 1 < ncnt) Ls[(lane + 2) * KLS] = e;  // ranks pos .. ncnt-2 move up by one (the last one falls off)
-  if (lane == pos) Ls[(pos + 1) * KLS] = key;
-  if (ncnt == k) {                                               // new worst: the key itself, or old rank k-2 moved up
-    const uint64_t up = __shfl_sync(FULL_MASK, e, k >= 2 ? k - 2 : 0);
-    worst = pos == k - 1 ? key : up;
-  }
-  return ncnt;
 }
 
 // k-list policy: ascending list for small k (short shifts, no sort at emit), 4-ary max-heap above
@@ -321,6 +288,12 @@ __host__ __device__ inline size_t klist_bytes(int k) {
 // 2: heap kernel too (+768 B of staging per warp: one resident warp fewer at k = 64).
 #ifndef TKNN_PAIR_LEAVES
 #define TKNN_PAIR_LEAVES 1
+#endif
+// Measured (profiles/r2_ab_pair.jsonl, r2_ab_pairfilter.jsonl; round 1 of cfg2 / cfg4): off 6.70 / 67.6 ms, on 6.50 / 65.2 ms,
+// on with the pair's filter in chunks of 8 (compile-time bit positions) 6.49 / 65.1 ms (default); chunks of 4 only in the
+// single-leaf filter as well: 6.70 / 67.2 ms — the unrolled chunks of 8 are worth 3 %.  Heap kernel (cfg3): 46.0 ms off, 49.2 on.
+#ifndef TKNN_PAIR_FILTER8
+#define TKNN_PAIR_FILTER8 1
 #endif
 __host__ __device__ constexpr bool pair_leaves(bool heap) { return TKNN_PAIR_LEAVES >= 2 || (TKNN_PAIR_LEAVES == 1 && !heap); }
 // points staged per warp = axis stride of the SoA staging area
@@ -406,13 +379,10 @@ __device__ __forceinline__ uint32_t filter4(const float* sx, int j0, float2 qx, 
   return m;
 }
 
-// Insert loop of the dense kernel: 1 (default) = every lane walks its own survivors and the warp reconverges once behind
-// the loop; 0 = warp-voted loop, one candidate per lane per iteration (round 1's form).  Measured (profiles/
-// r2_ab_insert.jsonl): cfg2 7.53 -> 7.35 ms, cfg3 48.95 -> 45.79 ms: the vote, its divergence check and the
-// reconvergence points cost ~10 of the ~100 warp instructions of an iteration.
-#ifndef TKNN_INSERT_LOOP
-#define TKNN_INSERT_LOOP 1
-#endif
+// Insert loop of the dense kernel: every lane walks its own survivors and the warp reconverges once behind the loop.
+// Round 1's warp-voted loop (one candidate per lane per iteration) cost ~10 of the ~100 warp instructions of an iteration in
+// the vote, its divergence check and the reconvergence points (profiles/r2_ab_insert.jsonl: cfg2 7.53 -> 7.35 ms, cfg3
+// 48.95 -> 45.79 ms); it was removed with the unification of the leaf section.
 // Worst entry of a full ascending list: 2 (default) = list_insert hands back the new tail, so the bound is updated from
 // registers, and the stored worst key is re-read only when a candidate TIES the bound (its index then decides);
 // 0 = re-read the tail slot before and after every insert (round 1); 1 = also keep the worst index in a register
@@ -563,10 +533,26 @@ static __global__ void __launch_bounds__(256, HEAP ? 1 : 5) traverse_kernel(cons
             __syncwarp();
             if (COUNT) { c_tests += valid ? cnt0 + cnt1 : 0; c_wleaves += 2; c_wpts += cnt0 + cnt1; }
             const float2 qx2 = make_float2(q.x, q.x), qy2 = make_float2(q.y, q.y), qz2 = make_float2(q.z, q.z);
+#if TKNN_PAIR_FILTER8
+            {
+              int j0 = 0;
+              for (; j0 + 8 <= cnt0; j0 += 8)
+                mask_a |= (filter4<NS>(soa, j0, qx2, qy2, qz2, bound) | (filter4<NS>(soa, j0 + 4, qx2, qy2, qz2, bound) << 4)) << j0;
+#pragma unroll 1
+              for (; j0 < cnt0; j0 += 4) mask_a |= filter4<NS>(soa, j0, qx2, qy2, qz2, bound) << j0;
+              j0 = 0;
+              for (; j0 + 8 <= cnt1; j0 += 8)
+                mask_b |= (filter4<NS>(soa + MAX_LEAF, j0, qx2, qy2, qz2, bound) |
+                           (filter4<NS>(soa + MAX_LEAF, j0 + 4, qx2, qy2, qz2, bound) << 4)) << j0;
+#pragma unroll 1
+              for (; j0 < cnt1; j0 += 4) mask_b |= filter4<NS>(soa + MAX_LEAF, j0, qx2, qy2, qz2, bound) << j0;
+            }
+#else
 #pragma unroll 1
             for (int j0 = 0; j0 < cnt0; j0 += 4) mask_a |= filter4<NS>(soa, j0, qx2, qy2, qz2, bound) << j0;
 #pragma unroll 1
             for (int j0 = 0; j0 < cnt1; j0 += 4) mask_b |= filter4<NS>(soa + MAX_LEAF, j0, qx2, qy2, qz2, bound) << j0;
+#endif
           } else {
             const bool second = (c == 1) != swap;  // false: child 0, true: child 1
             if (!leaf_wanted(second)) continue;
