@@ -88,14 +88,28 @@ static __global__ void __launch_bounds__(RADIX) scan_histogram_kernel(uint32_t* 
 // sat on the ranking loop's critical path — 38 % of the pass's stall samples (round-1 capture; the kernel as it is now:
 // profiles/r1_sort_v8_onesweep_ncu_summary.json, profiles/r2_build_onesweep_kernel_ncu_summary.json + _regions.txt).
 __device__ __forceinline__ uint32_t match_digit(uint32_t d) {
-  uint32_t peers = FULL_MASK;
+  // diff = lanes whose digit differs from mine in some bit.  Per bit: one predicate (and + setp fuse into LOP3.P), one vote,
+  // one select and ONE three-input LOP3 (diff | (ballot ^ mine)).  Written in PTX because the C form — in either the
+  // `peers &= bit ? m : ~m` or the `diff |= m ^ -bit` spelling — compiled to 6 instructions per bit (a shift, a mask, a
+  // compare and a negate around the vote).
+  uint32_t diff = 0;
 #pragma unroll
   for (int b = 0; b < RADIX_BITS; ++b) {
-    const bool bit = (d >> b) & 1u;
-    const uint32_t m = __ballot_sync(FULL_MASK, bit);
-    peers &= bit ? m : ~m;
+    uint32_t m, mine;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 t;\n\t"
+        "and.b32 t, %2, %3;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+        "selp.b32 %1, 0xffffffff, 0, p;\n\t"
+        "}"
+        : "=r"(m), "=r"(mine)
+        : "r"(d), "r"(1u << b));
+    diff |= m ^ mine;
   }
-  return peers;
+  return ~diff;
 }
 
 // One onesweep pass over the 8-bit digit at bit `shift`.
@@ -154,9 +168,15 @@ static __global__ void __launch_bounds__(THREADS, PAIRS ? TKNN_SORT_MINBLOCKS : 
     key[i] = ok ? keys_in[idx] : ~0ull;  // padding ranks after every real key of digit 255
     if (PAIRS) val[i] = ok ? vals_in[idx] : 0u;
   }
-  // early counts
+  // the digits, extracted once and kept four to a register; early counts
+  static_assert(ITEMS % 4 == 0, "digits are packed four to a register");
+  uint32_t dig[ITEMS / 4];
 #pragma unroll
-  for (int i = 0; i < ITEMS; ++i) atomicAdd(&s_warp_hist[warp][(uint32_t)(key[i] >> shift) & (RADIX - 1)], 1u);
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint32_t dg = (uint32_t)(key[i] >> shift) & (RADIX - 1);
+    dig[i >> 2] = (i & 3) ? (dig[i >> 2] | (dg << (8 * (i & 3)))) : dg;
+    atomicAdd(&s_warp_hist[warp][dg], 1u);
+  }
   __syncthreads();
 
   // thread d owns digit d: tile total -> aggregate, published at once
@@ -228,19 +248,17 @@ static __global__ void __launch_bounds__(THREADS, PAIRS ? TKNN_SORT_MINBLOCKS : 
   __syncthreads();
 
   // warp-local stable ranking straight into the sorted tile: lanes holding the same digit find each other (match_digit);
-  // the lowest of them advances the (warp, digit) counter for the whole peer group
+  // every lane reads its digit's (warp, digit) counter, then the lowest lane of each peer group advances it for the group
+  // (a read by all lanes and a predicated store instead of a leader's branch, read-modify-write and a shuffle)
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
-    const uint32_t dg = (uint32_t)(key[i] >> shift) & (RADIX - 1);
+    const uint32_t dg = (dig[i >> 2] >> (8 * (i & 3))) & (RADIX - 1);
     const uint32_t peers = match_digit(dg);
-    const int leader = __ffs(peers) - 1;
-    uint32_t old = 0;
-    if (lane == leader) {
-      old = s_warp_hist[warp][dg];
-      s_warp_hist[warp][dg] = old + __popc(peers);
-    }
-    old = __shfl_sync(FULL_MASK, old, leader);
-    const uint32_t pos = old + __popc(peers & lt_mask);
+    const uint32_t lower = peers & lt_mask;
+    const uint32_t old = s_warp_hist[warp][dg];
+    __syncwarp();
+    if (lower == 0u) s_warp_hist[warp][dg] = old + __popc(peers);
+    const uint32_t pos = old + __popc(lower);
     s_keys[pos] = key[i];
     if (PAIRS) s_vals[pos] = val[i];
     __syncwarp();
