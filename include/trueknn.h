@@ -69,7 +69,7 @@ enum {
                                   device->host copies overlap the search of the next slice (default 4; 1 = off) */
   ,TKNN_OPT_FILE_ORDER_CHUNKS = 12 /* tknn_search with HOST outputs: slices by original index (rows of a slice are
                                   contiguous and final), copies overlapped like above (default 0 = auto: 5, or 2 when
-                                  dist_out is NULL; 1 = off)   */
+                                  dist_out is NULL; for k > 24: 2 and 1; 1 = off)   */
   ,TKNN_OPT_MORTON_BITS = 13   /* curve-code bits per axis for the next build: 0 = auto (see TKNN_OPT_SORT_MODE), else 4..21 */
   ,TKNN_OPT_TIE_PRUNING = 14   /* index-aware pruning of exact distance ties: 0 = auto (kernel variant used when the
                                   build found leaves of coincident points), 1 = always, 2 = never           */

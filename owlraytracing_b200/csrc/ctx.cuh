@@ -60,7 +60,7 @@ struct tknn_ctx {
   int built_curve = 0;        // Hilbert levels the current BVH's keys were made with (0 = Morton): queries are coded alike
   int output_chunks = 4;  // host-output pipelining: slices whose D2H overlaps the next slice's search (1 = off)
   int file_order_chunks = 0;  // same for tknn_search (file-order rows): slices by original index (1 = off; 0 = auto: 5 with
-                              // distances, 2 indices-only — the sweeps of profiles/r2_e2e_mailbox.txt)
+                              // distances, 2 indices-only; k > 24: 2 and 1 — the sweeps of profiles/r2_e2e_mailbox.txt, r2_e2e_cfg3.txt)
   DevBuf chunk_queue;
   // Mailbox: 16 words of mapped pinned host memory that a one-thread kernel fills (fetch_words): the small read-backs of a
   // search or build (unresolved count, radius, leaf count, flags) then never queue behind a bulk device->host copy on the

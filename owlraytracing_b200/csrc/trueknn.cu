@@ -625,7 +625,11 @@ int tknn::host::search_range(tknn_ctx* c, int k, float start_radius, uint64_t q_
   // searched, so the step ends one slice-search after the link could have started: 5 slices with distances (cfg2: 21.2 /
   // 20.6 / 20.3 / 20.9 / 21.8 ms end to end with 3 / 4 / 5 / 6 / 8), 2 when only indices leave the device (17.9 / 16.5 / 16.9
   // ms with 1 / 2 / 3)
-  const int fo_chunks = c->file_order_chunks > 0 ? c->file_order_chunks : (dist_out ? 5 : 2);
+  // The heap kernel (k > 24) pays far more for a sparse slice (cfg3, k = 64: halves cost 1.7x per query, quarters 2.5x), so
+  // there the search is the slower side from three slices on: 140.2 / 136.0 / 136.5 / 144.6 ms with 1 / 2 / 3 / 4 slices, and
+  // 95.3 / 106.3 / 121.5 ms indices-only with 1 / 2 / 3 (profiles/r2_e2e_cfg3.txt).
+  const bool heap_k = k > trav::LIST_MAX_K;
+  const int fo_chunks = c->file_order_chunks > 0 ? c->file_order_chunks : (heap_k ? (dist_out ? 2 : 1) : (dist_out ? 5 : 2));
   if (chunks > 1) {
     while ((int)c->chunk_ev.size() < chunks) {
       cudaEvent_t e;
