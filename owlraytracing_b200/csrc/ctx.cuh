@@ -67,6 +67,7 @@ struct tknn_ctx {
   // copy engine, and never pass through pageable staging.
   uint32_t* mailbox_h = nullptr;
   uint32_t* mailbox_d = nullptr;
+  int mailbox_launches = 0;  // mailbox kernels since the counter was last folded into a launch count
   std::vector<cudaEvent_t> chunk_ev;
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> round_ev;

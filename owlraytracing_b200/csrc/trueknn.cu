@@ -494,6 +494,7 @@ int fetch_words(tknn_ctx* c, const uint32_t* a, int na, const uint32_t* b, int n
   if (c->mailbox_h) {
     mailbox_kernel<<<1, 1, 0, c->stream>>>(a, na, b, nb, c->mailbox_d);
     TK_CUDA(c, cudaGetLastError());
+    ++c->mailbox_launches;
     TK_CUDA(c, cudaStreamSynchronize(c->stream));
     for (int i = 0; i < na + nb; ++i) host_out[i] = c->mailbox_h[i];
     return TKNN_OK;
@@ -549,6 +550,7 @@ void reset_search_stats(tknn_ctx* c) {
   s.nodes_visited = s.points_tested = s.heap_inserts = 0;
   s.warp_node_visits = s.warp_leaf_visits = s.warp_point_loads = s.filter_violations = 0;
   s.d2h_bytes = 0;
+  c->mailbox_launches = 0;
 }
 
 }  // namespace
@@ -734,7 +736,7 @@ int tknn::host::search_range(tknn_ctx* c, int k, float start_radius, uint64_t q_
   TK_CUDA(c, cudaEventElapsedTime(&c->stats.search_ms, c->ev[0], c->ev[2]));
   TK_CUDA(c, cudaEventElapsedTime(&c->stats.d2h_ms, c->ev[2], c->ev[3]));
   if (start_radius > 0.0f) c->stats.estimate_ms = 0.f;
-  c->stats.kernel_launches = (uint32_t)launches;
+  c->stats.kernel_launches = (uint32_t)(launches + c->mailbox_launches + (c->mailbox_h ? 1 : 0));  // + the error-flag fetch below
   TK_TRY(finish_round_stats(c));
   TK_TRY(collect_counters(c));
   TK_TRY(read_error_flag(c));
@@ -912,6 +914,7 @@ int tknn::host::build_core(tknn_ctx* c, const float* xyz, uint64_t n, int dim, i
   c->n_leaves = 0;
   tknn_stats& S = c->stats;
   std::memset(&S, 0, sizeof(S));
+  c->mailbox_launches = 0;
   int launches = 0;
 
   // ---- stage the input ----
@@ -1065,7 +1068,7 @@ int tknn::host::build_core(tknn_ctx* c, const float* xyz, uint64_t n, int dim, i
   c->built_idx_bits = idx_bits;
   c->built_curve = c->curve ? hilbert_levels(n, mbits, c->curve_levels) : 0;
   c->has_dup_leaves = dupleaf != 0;
-  S.build_launches = (uint32_t)launches;
+  S.build_launches = (uint32_t)(launches + c->mailbox_launches);
   c->n = n;
   c->n_leaves = m;
   c->ids_in_w = ids_in_w;
@@ -1256,7 +1259,7 @@ int tknn_query(tknn_ctx* c, const float* queries, uint64_t nq, int dim, int stri
 #undef TK_BC
   TK_CUDA(c, cudaEventElapsedTime(&c->stats.search_ms, c->ev[0], c->ev[2]));
   TK_CUDA(c, cudaEventElapsedTime(&c->stats.d2h_ms, c->ev[2], c->ev[3]));
-  c->stats.kernel_launches = (uint32_t)launches;
+  c->stats.kernel_launches = (uint32_t)(launches + c->mailbox_launches + (c->mailbox_h ? 1 : 0));  // + the error-flag fetch below
   TK_TRY(finish_round_stats(c));
   TK_TRY(collect_counters(c));
   TK_TRY(read_error_flag(c));
