@@ -400,8 +400,11 @@ __device__ __forceinline__ uint32_t filter4(const float* sx, int j0, float2 qx, 
 // VARIANT: 0 = exact filter, 1 = conservative pre-filter (audited option), 2 = exact filter + index-aware
 // tie pruning (chosen by the host when the build found leaves of coincident points).
 // HEAP: k > LIST_MAX_K (compile-time, so the small-k kernel does not carry the heap code).
+// Launch bounds: the list kernels are capped at 48 registers (5 blocks of 8 warps = 40 resident warps; uncapped, the
+// unified leaf section compiles to 64 and loses a fifth of them); the heap kernels (12 resident warps: shared memory)
+// and the counting variants (diagnostics) take what they need.
 template <int MODE, bool COUNT, int VARIANT, bool HEAP>
-static __global__ void __launch_bounds__(256, HEAP ? 1 : 5) traverse_kernel(const Params P) {
+static __global__ void __launch_bounds__(256, (HEAP || COUNT) ? 1 : 5) traverse_kernel(const Params P) {
   constexpr bool APPROX = VARIANT == 1;
   constexpr bool TIES = VARIANT == 2 && MODE == MODE_KNN;
   extern __shared__ __align__(16) unsigned char smem[];
