@@ -72,7 +72,8 @@ enum {
                                   dist_out is NULL; for k > 24: 2 and 1; 1 = off)   */
   ,TKNN_OPT_MORTON_BITS = 13   /* curve-code bits per axis for the next build: 0 = auto (see TKNN_OPT_SORT_MODE), else 4..21 */
   ,TKNN_OPT_TIE_PRUNING = 14   /* index-aware pruning of exact distance ties: 0 = auto (kernel variant used when the
-                                  build found leaves of coincident points), 1 = always, 2 = never           */
+                                  build found a leaf of >= 8 coincident points, i.e. a duplicate cluster), 1 = always,
+                                  2 = never           */
   ,TKNN_OPT_WARP_ROUND_MAX = 15 /* rounds with at most this many active queries (the start-radius sample, late rounds of a
                                   few stragglers, small query sets) run one WARP per query (default 49152; 0 = never) */
   ,TKNN_OPT_CURVE = 16          /* space-filling curve the next build sorts the points by: 0 = Hilbert (default; consecutive

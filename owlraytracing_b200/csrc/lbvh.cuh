@@ -407,7 +407,7 @@ static __global__ void __launch_bounds__(THREADS) refit_kernel(const float4* __r
                                                         const int32_t* __restrict__ parent_node,
                                                         uint32_t* __restrict__ arrive, Node* nodes,
                                                         int* node_min_idx, uint32_t* __restrict__ dup_leaf_flag,
-                                                        float* __restrict__ scene_box) {
+                                                        uint32_t dup_min, float* __restrict__ scene_box) {
   const uint32_t leaf = blockIdx.x * THREADS + threadIdx.x;
   if (leaf >= n_leaves) return;
   const uint32_t b = leaf_start[leaf], e = leaf_start[leaf + 1];
@@ -419,8 +419,11 @@ static __global__ void __launch_bounds__(THREADS) refit_kernel(const float4* __r
     hi.x = fmaxf(hi.x, p.x); hi.y = fmaxf(hi.y, p.y); hi.z = fmaxf(hi.z, p.z);
     mn = min(mn, __float_as_int(p.w));
   }
-  // a leaf of >= 2 coincident points: the cloud has duplicate clusters; searches enable tie pruning
-  if (e - b >= 2 && lo.x == hi.x && lo.y == hi.y && lo.z == hi.z) *dup_leaf_flag = 1u;
+  // A leaf of >= dup_min coincident points: the cloud has duplicate CLUSTERS; searches enable tie pruning.  Tie pruning
+  // pays when a cluster fills many leaves (all at box distance == bound: D / 32 leaf visits per group without it); a few
+  // doubled points do not, and the pruning variant of the kernel costs 4.5 % on such a cloud (cfg3: 10 000 doubled points
+  // in 10 M, 46.3 ms with it, 44.2 ms without, the same node and test counts: profiles/r2_ab_ties_cfg3.jsonl).
+  if (e - b >= dup_min && lo.x == hi.x && lo.y == hi.y && lo.z == hi.z) *dup_leaf_flag = 1u;
   int32_t link = parent_leaf[leaf];
   for (;;) {
     const int node = link >> 1, slot = link & 1;

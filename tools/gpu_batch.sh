@@ -1,6 +1,14 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 400 python tools/e2e_sweep.py --cfg3 1 2 3 4 > gpurun_out/r2_e2e_cfg3.txt 2>&1
-timeout 300 python tools/e2e_sweep.py --cfg3 --idx-only 1 2 3 >> gpurun_out/r2_e2e_cfg3.txt 2>&1
-cat gpurun_out/r2_e2e_cfg3.txt
+OUT=gpurun_out/r2_ab_ties_cfg3.jsonl
+: > $OUT
+timeout 300 python tools/ab.py cfg3 libtrueknn.so libtrueknn.so:tie_pruning=2 >> $OUT 2>&1
+python - <<'PY'
+import json
+for l in open('gpurun_out/r2_ab_ties_cfg3.jsonl'):
+    try: d=json.loads(l)
+    except Exception: print(l[:300]); continue
+    if 'rc' in d: print(d); continue
+    print(d['workload'], d['lib'], d['opts'], 'search', d['search_ms'], 'kernels', d['kernel_ms'], 'tests/q', d['tests_per_q'], 'nodes/q', d['nodes_per_q'], d['brute_ok'], d['checksum'])
+PY
