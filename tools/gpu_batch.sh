@@ -1,14 +1,5 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-OUT=gpurun_out/r2_ab_ties_cfg3.jsonl
-: > $OUT
-timeout 300 python tools/ab.py cfg3 libtrueknn.so libtrueknn.so:tie_pruning=2 >> $OUT 2>&1
-python - <<'PY'
-import json
-for l in open('gpurun_out/r2_ab_ties_cfg3.jsonl'):
-    try: d=json.loads(l)
-    except Exception: print(l[:300]); continue
-    if 'rc' in d: print(d); continue
-    print(d['workload'], d['lib'], d['opts'], 'search', d['search_ms'], 'kernels', d['kernel_ms'], 'tests/q', d['tests_per_q'], 'nodes/q', d['nodes_per_q'], d['brute_ok'], d['checksum'])
-PY
+timeout 300 ncu --set full --clock-control none --import-source on -f -k regex:traverse_kernel -c 1 -o gpurun_out/r2_trav_cfg3_v12 python tools/ncu_target.py cfg3 > gpurun_out/ncu_trav_cfg3_v12.log 2>&1
+tail -1 gpurun_out/ncu_trav_cfg3_v12.log; ls -la gpurun_out/r2_trav_cfg3_v12.ncu-rep
