@@ -308,6 +308,12 @@ TKNN_API int tknn_multi_get_times(const tknn_multi* m, float* ms4);
 
 /* ---- introspection used by the tests and the bench (not part of the drop-in surface) ---- */
 
+/* The sort-key layout tknn_build would choose for n points under TKNN_OPT_MORTON_BITS = morton_bits (0 = auto) and
+ * TKNN_OPT_SORT_MODE = sort_mode: curve-code bits per axis, index bits packed below the code (0 = pair sort) and the
+ * number of 8-bit onesweep passes.  Pure host arithmetic: needs no context and no device. */
+TKNN_API int tknn_key_layout(uint64_t n, int morton_bits, int sort_mode, int* code_bits_per_axis, int* index_bits,
+                             int* sort_passes);
+
 /* Stand-alone onesweep radix sort of (u64 key, u32 value) pairs, stable, in place; device or host
  * pointers.  values == NULL: keys only (the kernel variant behind the builder's packed keys). */
 TKNN_API int tknn_sort_pairs(tknn_ctx* ctx, uint64_t* keys, uint32_t* values, uint64_t n);

@@ -97,7 +97,7 @@ EXPORTS = [
     "tknn_comm_unique_id", "tknn_comm_init", "tknn_get_dist_stats", "tknn_build_replicated", "tknn_partition_build",
     "tknn_partition_owned", "tknn_partition_search", "tknn_partition_verify", "tknn_create_multi", "tknn_multi_destroy",
     "tknn_multi_set_option", "tknn_multi_build", "tknn_multi_search", "tknn_multi_ranks", "tknn_multi_ctx",
-    "tknn_multi_last_error", "tknn_multi_get_times", "tknn_measure_smem_bandwidth",
+    "tknn_multi_last_error", "tknn_multi_get_times", "tknn_measure_smem_bandwidth", "tknn_key_layout",
 ]
 
 _lib = None
@@ -124,6 +124,7 @@ def load() -> C.CDLL:
     L.tknn_build.argtypes = [vp, vp, u64, C.c_int, C.c_int]
     L.tknn_search.argtypes = [vp, C.c_int, f32, vp, vp]
     L.tknn_search_shard.argtypes = [vp, C.c_int, f32, C.c_int, C.c_int, vp, vp, vp, C.POINTER(u64)]
+    L.tknn_key_layout.argtypes = [u64, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.tknn_shard_capacity.restype = u64
     L.tknn_shard_capacity.argtypes = [u64, C.c_int]
     L.tknn_query.argtypes = [vp, vp, u64, C.c_int, C.c_int, vp, vp, C.c_int, f32, vp, vp]

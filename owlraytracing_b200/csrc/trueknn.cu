@@ -446,17 +446,17 @@ int auto_morton_bits(uint64_t n) {
 // at 100 M points 9x — and one bit per axis less where that saves a whole pass and still leaves log2(n)/3 + 4.  Points
 // that share a cell are ordered by index: tree quality at the scale of one cell, never exactness.
 // *idx_bits == 0: pair sort.
-void choose_key_layout(const tknn_ctx* c, uint64_t n, int* mbits, int* idx_bits) {
+void key_layout(uint64_t n, int morton_bits, int sort_mode, int* mbits, int* idx_bits) {
   int lg = 0;
   while (((uint64_t)1 << lg) < n) ++lg;
   const int ib = std::max(1, lg), spacing = (lg + 2) / 3, fit = (64 - ib) / 3;
   *idx_bits = 0;
-  if (c->morton_bits > 0) {
-    *mbits = c->morton_bits;
-    if (c->sort_mode == 0 && 3 * c->morton_bits + ib <= 64) *idx_bits = ib;
+  if (morton_bits > 0) {
+    *mbits = morton_bits;
+    if (sort_mode == 0 && 3 * morton_bits + ib <= 64) *idx_bits = ib;
     return;
   }
-  if (c->sort_mode == 0 && fit >= spacing + 3) {
+  if (sort_mode == 0 && fit >= spacing + 3) {
     int b = std::min(13, fit);
     const int spare = 3 * b - 8 * ((3 * b - 1) / 8);  // code bits in the last, partial pass
     if (spare <= 3 && b - 1 >= spacing + 4) --b;
@@ -465,6 +465,10 @@ void choose_key_layout(const tknn_ctx* c, uint64_t n, int* mbits, int* idx_bits)
     return;
   }
   *mbits = auto_morton_bits(n);
+}
+
+void choose_key_layout(const tknn_ctx* c, uint64_t n, int* mbits, int* idx_bits) {
+  key_layout(n, c->morton_bits, c->sort_mode, mbits, idx_bits);
 }
 
 // Hilbert levels of the key kernel (lbvh.cuh: morton_kernel): two levels below the one where a cell holds one point
@@ -1081,6 +1085,15 @@ int tknn_search(tknn_ctx* c, int k, float start_radius, int32_t* idx_out, float*
   TK_TRY(check_ctx(c));
   ScopedDevice sd(c->device);
   return search_range(c, k, start_radius, 0, c->n, 0, nullptr, idx_out, dist_out, c->n);
+}
+
+int tknn_key_layout(uint64_t n, int morton_bits, int sort_mode, int* code_bits_per_axis, int* index_bits, int* sort_passes) {
+  if (n < 2 || n > rsort::MAX_N || morton_bits < 0 || morton_bits > 21 || (morton_bits > 0 && morton_bits < 4) ||
+      (sort_mode != 0 && sort_mode != 1) || !code_bits_per_axis || !index_bits || !sort_passes)
+    return TKNN_EINVAL;
+  key_layout(n, morton_bits, sort_mode, code_bits_per_axis, index_bits);
+  *sort_passes = (3 * *code_bits_per_axis + 7) / 8;
+  return TKNN_OK;
 }
 
 uint64_t tknn_shard_capacity(uint64_t n, int n_shards) {

@@ -391,3 +391,39 @@ def test_header_is_c99_and_links_from_plain_c(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "100"
+
+
+def test_key_layout_policy():
+    """tknn_key_layout (host arithmetic, no device): the packed (code << index bits | index) sort key fits 64 bits, keeps
+    at least log2(n)/3 + 3 code bits per axis, never needs more than five passes when packed, and falls back to the
+    (code, index) pair sort where that is impossible or not asked for."""
+    import ctypes as C
+    import math
+
+    from owlraytracing_b200 import _lib
+
+    L = _lib.load()
+
+    def layout(n, bits=0, mode=0):
+        b, i, p = C.c_int(-1), C.c_int(-1), C.c_int(-1)
+        rc = L.tknn_key_layout(n, bits, mode, C.byref(b), C.byref(i), C.byref(p))
+        return rc, b.value, i.value, p.value
+
+    assert layout(10_000_000) == (0, 13, 24, 5)        # cfg2: 39 code bits + 24 index bits
+    assert layout(100_000_000) == (0, 12, 27, 5)       # cfg4: 36 + 27
+    assert layout(100_000) == (0, 13, 17, 5)           # cfg1
+    assert layout(250_000_000)[2] == 0                 # a cfg5 rank: log2(n)/3 + 3 bits per axis do not fit beside 28 index bits
+    assert layout(10_000_000, mode=1) == (0, 16, 0, 6)  # round 1's pair sort
+    assert layout(10_000_000, bits=21) == (0, 21, 0, 8)  # more bits than fit beside the index: pairs
+    assert layout(10_000_000, bits=12) == (0, 12, 24, 5)
+    for n in [2, 3, 31, 32, 33, 1000, 4097, 2**20 - 1, 2**20, 2**20 + 1, 2**24, 2**24 + 1, 2**27, 2**28, 2**28 + 1, 2**30 - 1]:
+        rc, b, i, p = layout(n)
+        assert rc == 0 and 4 <= b <= 21 and p == (3 * b + 7) // 8
+        lg = max(1, math.ceil(math.log2(n)))
+        if i:
+            assert i == lg and (n - 1) < (1 << i)        # every index fits below the code
+            assert 3 * b + i <= 64 and p <= 5
+            assert b >= (lg + 2) // 3 + 3                # cells at least 8x finer per axis than the mean point spacing
+        else:
+            assert b == min(21, max(10, (lg + 2) // 3 + 8))
+    assert layout(1)[0] != 0 and layout(2**30)[0] != 0 and layout(1000, bits=3)[0] != 0 and layout(1000, mode=2)[0] != 0
